@@ -1,0 +1,153 @@
+"""Mirror of kernels/convolution_ops.py: same function names, argument order and error behaviour, backed by
+the fused sm_100a KPConv kernels through the C ABI (include/d3feat_b200.h).
+
+  unary_convolution(features, K_values)                                   convolution_ops.py:90-99
+  KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed='center',
+         KP_extent=1.0, KP_influence='linear', aggregation_mode='sum')    :102-158
+  KPConv_ops(q, s, idx, features, K_points, K_values, KP_extent, KP_influence, aggregation_mode)   :161-255
+  KPConv_deformable(..., modulated=False)                                 :258-376
+  KPConv_deform_ops(q, s, idx, features, K_points, offsets, modulations, K_values, KP_extent,
+                    KP_influence, mode)                                   :379-499
+
+Extensions (keyword-only, default off, so reference call sites work unchanged):
+  epilogue=(bn_scale, bn_shift, leaky_alpha)  -- fuse inference batch-norm + LeakyReLU into the kernel
+  residual=tensor                             -- (unary only) fused shortcut add before the LeakyReLU
+
+Tensors: contiguous CUDA float32 / int32. The kernel points of a KPConv are a restored, non-trainable
+variable in the reference (:145-148); here they come from the active ParamStore under
+'<scope>/kernel_points' or, without a store, from the seeded generator in synth.kernel_points.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from . import variables as V
+
+_INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
+_MODE = {"sum": 0, "closest": 1}
+
+
+def _epilogue_args(epilogue):
+    if epilogue is None:
+        return None, None, -1.0
+    scale, shift, alpha = epilogue
+    return scale, shift, (-1.0 if alpha is None else float(alpha))
+
+
+def unary_convolution(features, K_values, *, epilogue=None, residual=None):
+    """features[N,Cin] @ K_values[Cin,Cout] (tf.matmul, :90-99)."""
+    x = features.contiguous()
+    w = K_values.contiguous()
+    N, Cin = x.shape
+    Cout = w.shape[1]
+    if w.shape[0] != Cin:
+        raise ValueError("unary_convolution: features %s do not match K_values %s" % (tuple(x.shape), tuple(w.shape)))
+    scale, shift, alpha = _epilogue_args(epilogue)
+    out = torch.empty((N, Cout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().d3f_unary_forward(_lib.ptr(x), _lib.ptr(w), N, Cin, Cout, _lib.ptr(scale), _lib.ptr(shift),
+                                            None, _lib.ptr(residual.contiguous()) if residual is not None else None,
+                                            alpha, _lib.ptr(out), _lib.stream()), "d3f_unary_forward")
+    return out
+
+
+def _check_enums(KP_influence, aggregation_mode):
+    if KP_influence not in _INFLUENCE:
+        raise ValueError("Unknown influence function type (config.KP_influence)")          # :224, :469
+    if aggregation_mode not in _MODE:
+        raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")         # :232, :477
+
+
+def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
+               KP_influence, aggregation_mode, *, epilogue=None, bias=None):
+    """Rigid KPConv (:161-255): one fused launch sequence, no [N,H,K,*] intermediates."""
+    _check_enums(KP_influence, aggregation_mode)
+    q, s = query_points.contiguous(), support_points.contiguous()
+    idx, f = neighbors_indices.contiguous(), features.contiguous()
+    Kp, W = K_points.contiguous(), K_values.contiguous()
+    Nq, Ns, H = q.shape[0], s.shape[0], idx.shape[1]
+    K, Cin, Cout = W.shape
+    if f.shape[0] != Ns or f.shape[1] != Cin or Kp.shape[0] != K or idx.shape[0] != Nq:
+        raise ValueError("KPConv_ops: inconsistent shapes q%s s%s idx%s f%s Kp%s W%s" % (
+            tuple(q.shape), tuple(s.shape), tuple(idx.shape), tuple(f.shape), tuple(Kp.shape), tuple(W.shape)))
+    scale, shift, alpha = _epilogue_args(epilogue)
+    L = _lib.lib()
+    ws = _lib.workspace(L.d3f_kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout), q.device)
+    out = torch.empty((Nq, Cout), dtype=torch.float32, device=q.device)
+    _lib.check(L.d3f_kpconv_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp), _lib.ptr(W),
+                                    Nq, Ns, H, K, Cin, Cout, float(KP_extent), _INFLUENCE[KP_influence],
+                                    _MODE[aggregation_mode], 1, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(bias),
+                                    alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()),
+               "d3f_kpconv_forward")
+    return out
+
+
+def KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations,
+                      K_values, KP_extent, KP_influence, mode, *, epilogue=None):
+    """Deformable second stage (:379-499)."""
+    _check_enums(KP_influence, mode)
+    q, s = query_points.contiguous(), support_points.contiguous()
+    idx, f = neighbors_indices.contiguous(), features.contiguous()
+    Kp, W, off = K_points.contiguous(), K_values.contiguous(), offsets.contiguous()
+    mod = modulations.contiguous() if modulations is not None else None
+    Nq, Ns, H = q.shape[0], s.shape[0], idx.shape[1]
+    K, Cin, Cout = W.shape
+    scale, shift, alpha = _epilogue_args(epilogue)
+    L = _lib.lib()
+    ws = _lib.workspace(L.d3f_kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout), q.device)
+    out = torch.empty((Nq, Cout), dtype=torch.float32, device=q.device)
+    _lib.check(L.d3f_kpconv_deform_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp),
+                                           _lib.ptr(off), _lib.ptr(mod), _lib.ptr(W), Nq, Ns, H, K, Cin, Cout,
+                                           float(KP_extent), _INFLUENCE[KP_influence], _MODE[mode], _lib.ptr(scale),
+                                           _lib.ptr(shift), None, alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream()), "d3f_kpconv_deform_forward")
+    return out
+
+
+def _kernel_points(K_radius, num_kpoints, device, fixed):
+    store = V.current_store()
+    name = V.scoped("kernel_points")
+    if store is not None and name in store:
+        return store.get(name)
+    # no checkpoint: seeded stand-in for kernels/kernel_points.py:184-280 (random rotation + 1 % noise)
+    from .synth import kernel_points
+    seed = abs(hash(name)) % (2 ** 31)
+    return torch.from_numpy(kernel_points(np.random.default_rng(seed), K_radius, num_kpoints)).to(device)
+
+
+def KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed="center", KP_extent=1.0,
+           KP_influence="linear", aggregation_mode="sum", *, epilogue=None):
+    """:102-158 -- kernel-point disposition of radius 1.5*KP_extent, then KPConv_ops."""
+    K_radius = 1.5 * KP_extent
+    num_kpoints = int(K_values.shape[0])
+    K_points = _kernel_points(K_radius, num_kpoints, query_points.device, fixed)
+    return KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
+                      KP_influence, aggregation_mode, epilogue=epilogue)
+
+
+def KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values, fixed="center",
+                      KP_extent=1.0, KP_influence="linear", aggregation_mode="sum", modulated=False, *,
+                      epilogue=None):
+    """:258-376 -- rigid KPConv producing 3K (4K if modulated) offsets (+ bias), then the deformed conv."""
+    K_radius = 1.5 * KP_extent
+    num_kpoints = int(K_values.shape[0])
+    points_dim = int(query_points.shape[1])
+    K_points = _kernel_points(K_radius, num_kpoints, query_points.device, fixed)
+    store = V.current_store()
+    offset_dim = (points_dim + 1) * num_kpoints if modulated else points_dim * num_kpoints
+    w0_name, b0_name = V.scoped("offset_conv_weights"), V.scoped("offset_conv_bias")
+    if store is not None and w0_name in store:
+        K_values0, b0 = store.get(w0_name), store.get(b0_name)
+    else:                                                    # the reference initialises both to zero (:327-328)
+        K_values0 = torch.zeros((num_kpoints, K_values.shape[1], offset_dim), device=query_points.device)
+        b0 = torch.zeros((offset_dim,), device=query_points.device)
+    features0 = KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values0, KP_extent,
+                           KP_influence, aggregation_mode, bias=b0)
+    if modulated:
+        offsets = features0[:, :points_dim * num_kpoints].reshape(-1, num_kpoints, points_dim)
+        modulations = 2 * torch.sigmoid(features0[:, points_dim * num_kpoints:])
+    else:
+        offsets = features0.reshape(-1, num_kpoints, points_dim)
+        modulations = None
+    offsets = offsets * KP_extent
+    return KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets,
+                             modulations, K_values, KP_extent, KP_influence, aggregation_mode, epilogue=epilogue)

@@ -1,0 +1,344 @@
+// Radius neighbours on a sort-based hash grid over the supports (cell edge = radius * 1.001, 27-cell scan,
+// the three x-adjacent cells of a row are one contiguous run in the sorted order => 9 runs per query).
+//
+// Reference semantics (tf_custom_ops/tf_neighbors/neighbors/neighbors.cpp:211-332, nanoflann.hpp:249-253,
+// 432-440, 1280-1289): every support of the same cloud with d2 < r2, d2 = ((dx*dx)+dy*dy)+dz*dz evaluated in
+// fp32 with separately rounded mul/add (__fmul_rn/__fadd_rn: nvcc would otherwise contract to FMA),
+// r2 = radius*radius in fp32, rows ascending in (d2, index), padded with pad_value.
+#include "ops.cuh"
+#include "sort.cuh"
+
+namespace d3f {
+
+struct NbGrid {
+  float minx, miny, minz, inv_cell;
+  int nx, ny, nz;
+  long long ncells;  // per cloud
+};
+
+static NbGrid make_grid(const float* host_bbox, float radius) {
+  NbGrid g;
+  float cell = radius * 1.001f;
+  g.inv_cell = 1.0f / cell;
+  g.minx = host_bbox[0];
+  g.miny = host_bbox[1];
+  g.minz = host_bbox[2];
+  auto dim = [&](int a) {
+    double ext = (double)host_bbox[3 + a] - (double)host_bbox[a];
+    if (!(ext >= 0)) ext = 0;
+    double n = floor(ext / (double)cell) + 2.0;
+    return n > 2.0e9 ? 2000000000 : (int)n;
+  };
+  g.nx = dim(0);
+  g.ny = dim(1);
+  g.nz = dim(2);
+  g.ncells = (long long)g.nx * g.ny * g.nz;
+  return g;
+}
+
+constexpr long long kMaxGridCells = 1ll << 27;  // 128 Mi cells total (2 x 4 B tables = 1 GiB)
+
+__device__ __forceinline__ int cell_coord(float v, float mn, float inv, int n) {
+  int c = (int)floorf((v - mn) * inv);
+  return min(max(c, 0), n - 1);
+}
+
+__global__ void __launch_bounds__(256)
+support_key_kernel(const float* __restrict__ s, int Ns, const int* __restrict__ start, int B, NbGrid g,
+                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ns) return;
+  int b = batch_of(start, B, i);
+  int cx = cell_coord(s[3 * (size_t)i], g.minx, g.inv_cell, g.nx);
+  int cy = cell_coord(s[3 * (size_t)i + 1], g.miny, g.inv_cell, g.ny);
+  int cz = cell_coord(s[3 * (size_t)i + 2], g.minz, g.inv_cell, g.nz);
+  keys[i] = (uint64_t)b * (uint64_t)g.ncells + ((uint64_t)cz * g.ny + cy) * g.nx + cx;
+  vals[i] = (uint32_t)i;
+}
+
+// sorted_pts[i] = (x, y, z, bits(index)); cell_start/cell_end from run boundaries (tables pre-zeroed)
+__global__ void __launch_bounds__(256)
+grid_finalize_kernel(const float* __restrict__ s, const uint64_t* __restrict__ keys,
+                     const uint32_t* __restrict__ vals, int Ns, float4* __restrict__ sorted_pts,
+                     int* __restrict__ cell_start, int* __restrict__ cell_end) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Ns) return;
+  uint32_t p = vals[i];
+  sorted_pts[i] = make_float4(s[3 * (size_t)p], s[3 * (size_t)p + 1], s[3 * (size_t)p + 2], __uint_as_float(p));
+  uint64_t k = keys[i];
+  if (i == 0 || keys[i - 1] != k) cell_start[k] = i;
+  if (i == Ns - 1 || keys[i + 1] != k) cell_end[k] = i + 1;
+}
+
+struct NbWs {
+  SortBuffers sort;
+  int* s_start;   // [B+1]
+  int* q_start;   // [B+1] (count / fill)
+  float4* sorted_pts;
+  int* cell_start;
+  int* cell_end;
+};
+
+static size_t carve_nb(Carver& cv, int Ns, int B, long long total_cells, NbWs& w) {
+  int n = Ns > 0 ? Ns : 1;
+  w.sort.keys[0] = cv.take<uint64_t>(n);
+  w.sort.keys[1] = cv.take<uint64_t>(n);
+  w.sort.vals[0] = cv.take<uint32_t>(n);
+  w.sort.vals[1] = cv.take<uint32_t>(n);
+  w.sort.block_hist = cv.take<int>(256 * (size_t)sort_num_blocks(n));
+  w.s_start = cv.take<int>(B + 1);
+  w.q_start = cv.take<int>(B + 1);
+  w.sorted_pts = cv.take<float4>(n);
+  w.cell_start = cv.take<int>((size_t)total_cells + 1);
+  w.cell_end = cv.take<int>((size_t)total_cells + 1);
+  return cv.off;
+}
+
+size_t radius_neighbors_workspace_bytes(int Ns, int B, float radius, const float* host_bbox) {
+  if (host_bbox == nullptr || !(radius > 0.f) || B < 1) return 0;
+  NbGrid g = make_grid(host_bbox, radius);
+  long long total = g.ncells * B;
+  if (total > kMaxGridCells) return 0;
+  Carver cv(nullptr, ~(size_t)0);
+  NbWs w;
+  return carve_nb(cv, Ns, B, total, w) + 256;
+}
+
+int radius_neighbors_build(const float* supports, const int* s_batch_len, int B, int Ns, float radius,
+                           const float* host_bbox, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "radius_neighbors: B=%d must be in [1,%d]", B, kMaxBatch);
+  D3F_REQUIRE(radius > 0.f && Ns >= 0 && host_bbox != nullptr, D3F_ERR_INVALID,
+              "radius_neighbors: radius=%g Ns=%d invalid or host_bbox missing", (double)radius, Ns);
+  NbGrid g = make_grid(host_bbox, radius);
+  long long total = g.ncells * B;
+  D3F_REQUIRE(total <= kMaxGridCells, D3F_ERR_CAPACITY,
+              "radius_neighbors: grid %d x %d x %d x %d clouds exceeds %lld cells", g.nx, g.ny, g.nz, B,
+              kMaxGridCells);
+  D3F_REQUIRE(workspace_bytes >= radius_neighbors_workspace_bytes(Ns, B, radius, host_bbox), D3F_ERR_WORKSPACE,
+              "radius_neighbors: workspace too small");
+  Carver cv(workspace, workspace_bytes);
+  NbWs w;
+  carve_nb(cv, Ns, B, total, w);
+  if (launch_batch_start(s_batch_len, B, w.s_start, stream)) return D3F_ERR_CUDA;
+  D3F_CUDA(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * ((size_t)total + 1), stream));
+  D3F_CUDA(cudaMemsetAsync(w.cell_end, 0, sizeof(int) * ((size_t)total + 1), stream));
+  if (Ns == 0) return D3F_OK;
+  support_key_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, w.s_start, B, g, w.sort.keys[0],
+                                                            w.sort.vals[0]);
+  D3F_LAUNCH_CHECK("support_key_kernel");
+  int bits = 1;
+  while (bits < 62 && (1ll << bits) < total) ++bits;
+  int cur = radix_sort_pairs(w.sort, Ns, bits, stream);
+  if (cur < 0) return cur;
+  grid_finalize_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, w.sort.keys[cur], w.sort.vals[cur], Ns,
+                                                              w.sorted_pts, w.cell_start, w.cell_end);
+  D3F_LAUNCH_CHECK("grid_finalize_kernel");
+  return D3F_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+constexpr int kNbWarps = 8;      // warps (= queries in flight) per CTA
+constexpr int kNbListCap = 512;  // hits kept in shared memory per query before the generic path
+
+struct Hit {
+  float d2;
+  int idx;
+};
+
+__device__ __forceinline__ bool hit_less(float da, int ia, float db, int ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+__device__ __forceinline__ float sq_dist_rn(float qx, float qy, float qz, float4 s) {
+  float dx = __fsub_rn(qx, s.x), dy = __fsub_rn(qy, s.y), dz = __fsub_rn(qz, s.z);
+  float r = __fmul_rn(dx, dx);
+  r = __fadd_rn(r, __fmul_rn(dy, dy));
+  r = __fadd_rn(r, __fmul_rn(dz, dz));
+  return r;
+}
+
+// FILL = false: counts only. FILL = true: sorted rows.
+template <bool FILL>
+__global__ void __launch_bounds__(kNbWarps * 32)
+radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ q_start, int B, NbGrid g,
+                    const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start,
+                    const int* __restrict__ cell_end, float r2, int cols, int pad_value,
+                    int* __restrict__ counts, int* __restrict__ out_max, int* __restrict__ out_idx) {
+  __shared__ int run_start[kNbWarps][9];
+  __shared__ int run_prefix[kNbWarps][10];
+  __shared__ Hit list[FILL ? kNbWarps : 1][FILL ? kNbListCap : 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x * kNbWarps + warp;
+  if (qi >= Nq) return;  // warp-uniform
+  const float qx = q[3 * (size_t)qi], qy = q[3 * (size_t)qi + 1], qz = q[3 * (size_t)qi + 2];
+  const int b = batch_of(q_start, B, qi);
+  const int cx = cell_coord(qx, g.minx, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.miny, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.minz, g.inv_cell, g.nz);
+
+  // lanes 0..8: one (dy,dz) row each -> contiguous run over cells cx-1..cx+1
+  int rs = 0, rl = 0;
+  if (lane < 9) {
+    int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+    if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+      long long row = (long long)b * g.ncells + ((long long)zz * g.ny + yy) * g.nx;
+      int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+      int s = 0x7fffffff, e = 0;
+      for (int x = x0; x <= x1; ++x) {
+        int cs = cell_start[row + x], ce = cell_end[row + x];
+        if (ce > cs) {
+          s = min(s, cs);
+          e = max(e, ce);
+        }
+      }
+      if (e > s) {
+        rs = s;
+        rl = e - s;
+      }
+    }
+  }
+  int inc = rl;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane < 9) {
+    run_start[warp][lane] = rs;
+    run_prefix[warp][lane + 1] = inc;
+  }
+  if (lane == 0) run_prefix[warp][0] = 0;
+  __syncwarp();
+  const int T = run_prefix[warp][9];
+
+  int n = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    int t = t0 + lane;
+    bool hit = false;
+    float d2 = 0.f;
+    int sidx = 0;
+    if (t < T) {
+      int r = 0;
+#pragma unroll
+      for (int k = 1; k < 9; ++k) r += (t >= run_prefix[warp][k]) ? 1 : 0;
+      float4 sp = sorted_pts[run_start[warp][r] + (t - run_prefix[warp][r])];
+      d2 = sq_dist_rn(qx, qy, qz, sp);
+      sidx = (int)__float_as_uint(sp.w);
+      hit = d2 < r2;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (FILL) {
+      int pos = n + __popc(m & ((1u << lane) - 1u));
+      if (hit && pos < kNbListCap) {
+        list[warp][pos].d2 = d2;
+        list[warp][pos].idx = sidx;
+      }
+    }
+    n += __popc(m);
+  }
+
+  if (!FILL) {
+    if (lane == 0) {
+      counts[qi] = n;
+      atomicMax(out_max, n);
+    }
+    return;
+  }
+  if (counts != nullptr && lane == 0) counts[qi] = n;
+  if (out_max != nullptr && lane == 0) atomicMax(out_max, n);
+  __syncwarp();
+  int* row = out_idx + (size_t)qi * cols;
+  if (n <= kNbListCap) {
+    // rank sort: rank = number of hits that precede in (d2, idx)
+    for (int j = lane; j < n; j += 32) {
+      float dj = list[warp][j].d2;
+      int ij = list[warp][j].idx;
+      int rank = 0;
+      for (int k = 0; k < n; ++k) rank += hit_less(list[warp][k].d2, list[warp][k].idx, dj, ij) ? 1 : 0;
+      if (rank < cols) row[rank] = ij;
+    }
+  } else {
+    // generic path for very dense rows: emit the nearest `cols` one at a time by re-scanning the runs
+    float last_d = -1.f;
+    int last_i = -1;
+    int emit = min(n, cols);
+    for (int c = 0; c < emit; ++c) {
+      float best_d = 3.0e38f;
+      int best_i = 0x7fffffff;
+      for (int t = lane; t < T; t += 32) {
+        int r = 0;
+#pragma unroll
+        for (int k = 1; k < 9; ++k) r += (t >= run_prefix[warp][k]) ? 1 : 0;
+        float4 sp = sorted_pts[run_start[warp][r] + (t - run_prefix[warp][r])];
+        float d2 = sq_dist_rn(qx, qy, qz, sp);
+        int si = (int)__float_as_uint(sp.w);
+        if (d2 < r2 && hit_less(last_d, last_i, d2, si) && hit_less(d2, si, best_d, best_i)) {
+          best_d = d2;
+          best_i = si;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float od = __shfl_xor_sync(0xffffffffu, best_d, o);
+        int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (hit_less(od, oi, best_d, best_i)) {
+          best_d = od;
+          best_i = oi;
+        }
+      }
+      if (lane == 0) row[c] = best_i;
+      last_d = best_d;
+      last_i = best_i;
+    }
+  }
+  for (int c = n + lane; c < cols; c += 32) row[c] = pad_value;
+}
+
+static int query_common(bool fill, const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
+                        const float* host_bbox, const void* workspace, int cols, int pad_value, int* counts,
+                        int* out_max, int* out_idx, cudaStream_t stream) {
+  D3F_REQUIRE(B >= 1 && B <= kMaxBatch && Nq >= 0 && radius > 0.f && host_bbox != nullptr, D3F_ERR_INVALID,
+              "radius_neighbors: invalid arguments (B=%d Nq=%d radius=%g)", B, Nq, (double)radius);
+  NbGrid g = make_grid(host_bbox, radius);
+  long long total = g.ncells * B;
+  D3F_REQUIRE(total <= kMaxGridCells, D3F_ERR_CAPACITY, "radius_neighbors: grid too large");
+  Carver cv(const_cast<void*>(workspace), ~(size_t)0);
+  NbWs w;
+  carve_nb(cv, Ns, B, total, w);
+  if (launch_batch_start(q_batch_len, B, w.q_start, stream)) return D3F_ERR_CUDA;
+  if (out_max != nullptr && !fill) D3F_CUDA(cudaMemsetAsync(out_max, 0, sizeof(int), stream));
+  if (Nq == 0) return D3F_OK;
+  float r2 = radius * radius;  // neighbors.cpp:226 (fp32 product)
+  int blocks = ceil_div(Nq, kNbWarps);
+  if (fill) {
+    radius_query_kernel<true><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, w.q_start, B, g, w.sorted_pts,
+                                                                    w.cell_start, w.cell_end, r2, cols, pad_value,
+                                                                    counts, out_max, out_idx);
+  } else {
+    radius_query_kernel<false><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, w.q_start, B, g, w.sorted_pts,
+                                                                     w.cell_start, w.cell_end, r2, 0, 0, counts,
+                                                                     out_max, nullptr);
+  }
+  D3F_LAUNCH_CHECK("radius_query_kernel");
+  return D3F_OK;
+}
+
+int radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
+                           const float* host_bbox, const void* workspace, int* counts, int* out_max,
+                           cudaStream_t stream) {
+  D3F_REQUIRE(counts != nullptr && out_max != nullptr, D3F_ERR_INVALID, "radius_neighbors_count: null output");
+  return query_common(false, queries, q_batch_len, Nq, B, Ns, radius, host_bbox, workspace, 0, 0, counts, out_max,
+                      nullptr, stream);
+}
+
+int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
+                          const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
+                          cudaStream_t stream) {
+  D3F_REQUIRE(cols >= 0 && (out_idx != nullptr || cols == 0 || Nq == 0), D3F_ERR_INVALID,
+              "radius_neighbors_fill: cols=%d / null output", cols);
+  if (cols == 0) return D3F_OK;
+  return query_common(true, queries, q_batch_len, Nq, B, Ns, radius, host_bbox, workspace, cols, pad_value, nullptr,
+                      nullptr, out_idx, stream);
+}
+
+}  // namespace d3f

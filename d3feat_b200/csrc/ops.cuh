@@ -1,0 +1,55 @@
+// Internal (C++) interface between the translation units of the library. The public C ABI is api.cu.
+#pragma once
+#include "common.cuh"
+
+namespace d3f {
+
+// ---- gemm.cu ----------------------------------------------------------------------------------------
+struct Epilogue {
+  const float* rowscale;  // [M] or null
+  const float* bn_scale;  // [N] or null
+  const float* bn_shift;  // [N] or null (used with bn_scale)
+  const float* bias;      // [N] or null
+  const float* residual;  // [M,N] or null
+  float leaky_alpha;      // < 0: none
+};
+int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
+
+// ---- grid.cu ----------------------------------------------------------------------------------------
+int launch_batch_start(const int* len, int B, int* start, cudaStream_t stream);
+int bbox_device(const float* pts, int N, float* out_bbox, cudaStream_t stream);
+size_t grid_subsample_workspace_bytes(int N, int B);
+int grid_subsample(const float* pts, const int* batch_len, int B, int N, float dl, const float* feats, int fdim,
+                   const int* classes, int ldim, const float* host_bbox, float* out_pts, float* out_feats,
+                   int* out_classes, int* out_batch_len, int* out_M, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+
+// ---- neighbors.cu -----------------------------------------------------------------------------------
+size_t radius_neighbors_workspace_bytes(int Ns, int B, float radius, const float* host_bbox);
+int radius_neighbors_build(const float* supports, const int* s_batch_len, int B, int Ns, float radius,
+                           const float* host_bbox, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
+                           const float* host_bbox, const void* workspace, int* counts, int* out_max,
+                           cudaStream_t stream);
+int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
+                          const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
+                          cudaStream_t stream);
+
+// ---- kpconv.cu --------------------------------------------------------------------------------------
+size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
+int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* idx, const float* feat,
+                        const float* Kp, const float* offsets, const float* modulations, const float* W, int Nq,
+                        int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, int normalize,
+                        const float* bn_scale, const float* bn_shift, const float* bias, float leaky_alpha,
+                        float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// ---- pool.cu ----------------------------------------------------------------------------------------
+int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream);
+int closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C, float* out,
+                 cudaStream_t stream);
+int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream_t stream);
+int affine_leaky(const float* x, int N, int C, const float* scale, const float* shift, const float* residual,
+                 float alpha, float* out, cudaStream_t stream);
+
+}  // namespace d3f

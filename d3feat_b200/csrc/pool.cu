@@ -1,0 +1,157 @@
+// Indexed pooling kernels of the encoder / decoder:
+//   ind_max_pool  models/network_blocks.py:51-66   shadow row = column-wise minimum of x
+//   closest_pool  models/network_blocks.py:69-83   shadow row = zeros, first index column only
+//   l2_normalize  models/D3Feat.py:65              x * rsqrt(max(sum x^2, eps))
+#include "ops.cuh"
+
+namespace d3f {
+
+// column-wise minimum via ordered-uint atomics; colmin_ord pre-set to 0xFFFFFFFF
+__global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x, int N, int C,
+                                                     unsigned* __restrict__ colmin_ord) {
+  __shared__ unsigned red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  unsigned m = 0xffffffffu;
+  if (c < C)
+    for (int r = blockIdx.y * 8 + ty; r < N; r += gridDim.y * 8) m = min(m, f2ord(x[(size_t)r * C + c]));
+  red[ty][tx] = m;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m = min(m, red[k][tx]);
+    atomicMin(&colmin_ord[c], m);
+  }
+}
+
+// one warp per pooled row; lanes stride the channels (float4 when C % 4 == 0)
+template <int VEC>
+__global__ void __launch_bounds__(256)
+ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1, int N2, int H, int C,
+                    const unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N2) return;
+  const int* row = inds + (size_t)warp * H;
+  for (int c0 = lane * VEC; c0 < C; c0 += 32 * VEC) {
+    float best[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) best[v] = -3.402823466e38f;
+    bool any_shadow = false;
+    for (int h = 0; h < H; ++h) {
+      int id = row[h];
+      if (id < 0 || id >= N1) {
+        any_shadow = true;
+        continue;
+      }
+      const float* p = x + (size_t)id * C + c0;
+      if (VEC == 4) {
+        float4 t = *reinterpret_cast<const float4*>(p);
+        best[0] = fmaxf(best[0], t.x); best[1 % VEC] = fmaxf(best[1 % VEC], t.y);
+        best[2 % VEC] = fmaxf(best[2 % VEC], t.z); best[3 % VEC] = fmaxf(best[3 % VEC], t.w);
+      } else {
+        best[0] = fmaxf(best[0], *p);
+      }
+    }
+    if (any_shadow || H == 0) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (c0 + v < C) best[v] = fmaxf(best[v], ord2f(colmin_ord[c0 + v]));
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(out + (size_t)warp * C + c0) =
+          make_float4(best[0], best[1 % VEC], best[2 % VEC], best[3 % VEC]);
+    } else {
+      out[(size_t)warp * C + c0] = best[0];
+    }
+  }
+}
+
+int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,
+                 size_t workspace_bytes, cudaStream_t stream) {
+  D3F_REQUIRE(N1 >= 1 && N2 >= 0 && H >= 0 && C >= 1, D3F_ERR_INVALID, "ind_max_pool: bad shape N1=%d N2=%d H=%d C=%d",
+              N1, N2, H, C);
+  D3F_REQUIRE(workspace_bytes >= sizeof(unsigned) * (size_t)C, D3F_ERR_WORKSPACE, "ind_max_pool: workspace too small");
+  if (N2 == 0) return D3F_OK;
+  unsigned* colmin = (unsigned*)workspace;
+  D3F_CUDA(cudaMemsetAsync(colmin, 0xff, sizeof(unsigned) * C, stream));
+  dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 8), 64));
+  colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, C, colmin);
+  D3F_LAUNCH_CHECK("colmin_kernel");
+  int blocks = ceil_div(N2 * 32, 256);
+  bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (v4) ind_max_pool_kernel<4><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, H, C, colmin, out);
+  else ind_max_pool_kernel<1><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, H, C, colmin, out);
+  D3F_LAUNCH_CHECK("ind_max_pool_kernel");
+  return D3F_OK;
+}
+
+__global__ void __launch_bounds__(256)
+closest_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1, int N2, int ld, int C,
+                    float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N2) return;
+  int id = inds[(size_t)warp * ld];
+  bool shadow = id < 0 || id >= N1;
+  for (int c = lane; c < C; c += 32) out[(size_t)warp * C + c] = shadow ? 0.f : x[(size_t)id * C + c];
+}
+
+int closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C, float* out, cudaStream_t stream) {
+  D3F_REQUIRE(N1 >= 0 && N2 >= 0 && ld_inds >= 1 && C >= 1, D3F_ERR_INVALID, "closest_pool: bad shape");
+  if (N2 == 0) return D3F_OK;
+  closest_pool_kernel<<<ceil_div(N2 * 32, 256), 256, 0, stream>>>(x, inds, N1, N2, ld_inds, C, out);
+  D3F_LAUNCH_CHECK("closest_pool_kernel");
+  return D3F_OK;
+}
+
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, int N, int C, float eps,
+                                                           float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float v = x[(size_t)warp * C + c];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float inv = rsqrtf(fmaxf(s, eps));
+  // one Newton step: rsqrtf is 2 ulp, the reference divides by an IEEE sqrt
+  float m = fmaxf(s, eps);
+  inv = inv * (1.5f - 0.5f * m * inv * inv);
+  for (int c = lane; c < C; c += 32) out[(size_t)warp * C + c] = x[(size_t)warp * C + c] * inv;
+}
+
+int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream_t stream) {
+  D3F_REQUIRE(N >= 0 && C >= 1, D3F_ERR_INVALID, "l2_normalize: bad shape");
+  if (N == 0) return D3F_OK;
+  l2_normalize_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(x, N, C, eps, out);
+  D3F_LAUNCH_CHECK("l2_normalize_kernel");
+  return D3F_OK;
+}
+
+__global__ void __launch_bounds__(256)
+affine_leaky_kernel(const float* __restrict__ x, long long total, int C, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ residual, float alpha,
+                    float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float y = x[i];
+    if (scale) y = fmaf(y, scale[c], shift[c]);
+    if (residual) y += residual[i];
+    if (alpha >= 0.f) y = y > 0.f ? y : y * alpha;
+    out[i] = y;
+  }
+}
+
+int affine_leaky(const float* x, int N, int C, const float* scale, const float* shift, const float* residual,
+                 float alpha, float* out, cudaStream_t stream) {
+  D3F_REQUIRE(N >= 0 && C >= 1 && (scale == nullptr) == (shift == nullptr), D3F_ERR_INVALID, "affine_leaky: bad arguments");
+  long long total = (long long)N * C;
+  if (total == 0) return D3F_OK;
+  int blocks = (int)min((total + 255) / 256, (long long)kNumSMs * 16);
+  affine_leaky_kernel<<<blocks, 256, 0, stream>>>(x, total, C, scale, shift, residual, alpha, out);
+  D3F_LAUNCH_CHECK("affine_leaky_kernel");
+  return D3F_OK;
+}
+
+}  // namespace d3f

@@ -1,0 +1,172 @@
+/* d3feat_b200 -- C ABI of the Blackwell-native (sm_100a) D3Feat hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / TF types. Every entry point
+ *   - takes DEVICE pointers unless a parameter is explicitly marked "host",
+ *   - takes an explicit CUDA stream (cudaStream_t passed as void*), enqueues its work there and
+ *     returns without synchronising unless stated otherwise,
+ *   - never frees or allocates caller-visible memory: scratch comes from the caller-supplied
+ *     workspace (size from the matching *_workspace_bytes query),
+ *   - returns 0 (D3F_OK) or a negative D3F_ERR_* code; d3f_last_error() gives the message
+ *     (thread-local). No exception crosses the boundary.
+ *   - keeps no global mutable state: re-entrant across host threads and streams (the reference's
+ *     OpKernels are invoked concurrently by the tf.data map pool, datasets/common.py:600,744).
+ *
+ * Reference interfaces replaced (paths relative to the D3Feat repository):
+ *   d3f_grid_subsample        tf_custom_ops/tf_subsampling/tf_batch_subsampling.cpp:8-20,30-122
+ *                             tf_custom_ops/tf_subsampling/tf_subsampling.cpp:8-17 (B = 1)
+ *                             cpp_wrappers/cpp_subsampling/wrapper.cpp:58-286 (features / classes)
+ *   d3f_radius_neighbors_*    tf_custom_ops/tf_neighbors/tf_batch_neighbors.cpp:8-30,40-116
+ *                             tf_custom_ops/tf_neighbors/tf_neighbors.cpp:8-18 (B = 1, pad = -1)
+ *   d3f_kpconv_forward        kernels/convolution_ops.py:161-255 (KPConv_ops) + BN/LeakyReLU epilogue
+ *                             models/network_blocks.py:149-165,185-186
+ *   d3f_kpconv_deform_forward kernels/convolution_ops.py:379-499 (KPConv_deform_ops)
+ *   d3f_unary_forward         kernels/convolution_ops.py:90-99 + models/network_blocks.py:207-219,
+ *                             :343-368 (conv3 + shortcut add + LeakyReLU)
+ *   d3f_ind_max_pool          models/network_blocks.py:51-66
+ *   d3f_closest_pool          models/network_blocks.py:69-83
+ *   d3f_l2_normalize          models/D3Feat.py:65
+ */
+#ifndef D3FEAT_B200_H_
+#define D3FEAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3F_OK 0
+#define D3F_ERR_INVALID (-1)   /* bad argument (shape, enum, null pointer)            */
+#define D3F_ERR_CAPACITY (-2)  /* caller-supplied output capacity / grid budget too small */
+#define D3F_ERR_CUDA (-3)      /* CUDA runtime error (message in d3f_last_error)       */
+#define D3F_ERR_WORKSPACE (-4) /* workspace smaller than *_workspace_bytes             */
+
+/* KP_influence / aggregation_mode enums (kernels/convolution_ops.py:208-232) */
+#define D3F_INFLUENCE_CONSTANT 0
+#define D3F_INFLUENCE_LINEAR 1
+#define D3F_INFLUENCE_GAUSSIAN 2
+#define D3F_MODE_SUM 0
+#define D3F_MODE_CLOSEST 1
+
+typedef void* d3f_stream_t; /* cudaStream_t */
+
+int d3f_version(void);
+const char* d3f_last_error(void);
+/* number of kernels this library has launched from the calling host thread (bench.py "gpu_launches") */
+long long d3f_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bounding box of a stacked cloud: out_bbox[6] = {minx,miny,minz,maxx,maxy,maxz} (device floats).
+ * Used to bound the hash grids of the two ops below without a host round trip per call.
+ * ------------------------------------------------------------------------------------------- */
+int d3f_bbox(const float* pts, int N, float* out_bbox, d3f_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Grid subsampling (voxel barycenters), stacked clouds.
+ *   pts[N,3], batch_len[B] (device int32), dl: cell size.
+ *   feats[N,fdim] / classes[N,ldim] optional (NULL, 0): the cpp_wrappers signature.
+ *   host_bbox: host float[6] bounding ALL points (from d3f_bbox or known a priori). It only bounds
+ *     the sort-key width; the per-cloud origin is recomputed exactly on the device.
+ *   Outputs (capacity N rows each): out_pts[<=N,3], out_feats, out_classes, out_batch_len[B],
+ *     out_M[1] (device int32: total number of cells). Cells are emitted per cloud in ascending
+ *     reference cell key iX + NX*iY + NX*NY*iZ (grid_subsampling.cpp:53-56); barycenters are
+ *     bit-identical to the reference (fp32 sums in input order, * (float)(1.0/count)).
+ *   classes follow the reference literally: the LARGEST label present in the cell
+ *     (std::max_element over map pairs, grid_subsampling.cpp:97-101).
+ * ------------------------------------------------------------------------------------------- */
+size_t d3f_grid_subsample_workspace_bytes(int N, int B);
+int d3f_grid_subsample(const float* pts, const int* batch_len, int B, int N, float dl,
+                       const float* feats, int fdim, const int* classes, int ldim,
+                       const float* host_bbox, float* out_pts, float* out_feats, int* out_classes,
+                       int* out_batch_len, int* out_M, void* workspace, size_t workspace_bytes,
+                       d3f_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Radius neighbours, stacked clouds (hash grid over the supports, 27-cell scan per query).
+ *   Result-set semantics of the reference (neighbors.cpp:211-332 / nanoflann.hpp:249-253,432-440):
+ *   supports of the same cloud with d2 < radius*radius, d2 = ((dx*dx)+dy*dy)+dz*dz in fp32 without
+ *   FMA contraction, rows sorted by ascending (d2, index), global support indices, rows padded with
+ *   pad_value (Ns for the batch op, -1 for the non-batch op).
+ *
+ *   Two-phase use for the exact reference shape [Nq, max count]:
+ *     d3f_radius_neighbors_build  -> grid over the supports in `workspace`
+ *     d3f_radius_neighbors_count  -> counts[Nq] and out_max[1] (device); caller reads out_max
+ *     d3f_radius_neighbors_fill   -> out_idx[Nq, cols]; rows longer than cols keep the nearest cols
+ *   Single-phase use with a known column cap (the pyramid's neighborhood_limits,
+ *   datasets/common.py:399-406): build + fill with cols = cap (count optional).
+ * ------------------------------------------------------------------------------------------- */
+size_t d3f_radius_neighbors_workspace_bytes(int Ns, int B, float radius, const float* host_bbox);
+int d3f_radius_neighbors_build(const float* supports, const int* s_batch_len, int B, int Ns,
+                               float radius, const float* host_bbox, void* workspace,
+                               size_t workspace_bytes, d3f_stream_t stream);
+int d3f_radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq,
+                               const float* supports, const int* s_batch_len, int B, int Ns,
+                               float radius, const float* host_bbox, const void* workspace,
+                               int* counts, int* out_max, d3f_stream_t stream);
+int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq,
+                              const float* supports, const int* s_batch_len, int B, int Ns,
+                              float radius, const float* host_bbox, const void* workspace, int cols,
+                              int pad_value, int* out_idx, d3f_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rigid KPConv forward (KPConv_ops, convolution_ops.py:161-255), fused with the block epilogue.
+ *   q[Nq,3], s[Ns,3], idx[Nq,H] (shadow index = Ns), feat[Ns,Cin], Kp[K,3], W[K,Cin,Cout].
+ *   out[Nq,Cout] = epilogue( (sum_k (sum_h w[n,h,k] feat[idx[n,h]]) W_k) / nn[n] )
+ *   nn = max(#neighbours whose feature-row sum > 0, 1)   (normalize != 0; :249-253)
+ *   epilogue: y = x*bn_scale[c] + bn_shift[c] (if bn_scale != NULL; inference batch norm folded by
+ *   the caller: scale = gamma/sqrt(var+1e-6), shift = beta - mean*scale), then + bias[c] (if
+ *   bias != NULL), then LeakyReLU(leaky_alpha) if leaky_alpha >= 0 (pass -1 for none).
+ *   shadow_xyz: coordinate of the shadow support (1e6 rigid :190, 1000 deformable :414).
+ * ------------------------------------------------------------------------------------------- */
+size_t d3f_kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
+int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const float* feat,
+                       const float* Kp, const float* W, int Nq, int Ns, int H, int K, int Cin,
+                       int Cout, float extent, int influence, int mode, int normalize,
+                       const float* bn_scale, const float* bn_shift, const float* bias,
+                       float leaky_alpha, float* out, void* workspace, size_t workspace_bytes,
+                       d3f_stream_t stream);
+
+/* Deformable KPConv second stage (KPConv_deform_ops, :379-499): per-query kernel points
+ * Kp + offsets[n,K,3]; influence distance /extent (no factor 2); neighbours in range of no kernel
+ * point are dropped (:435-451); optional modulations[n,K]; no neighbour-count normalisation. */
+int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, const float* feat,
+                              const float* Kp, const float* offsets, const float* modulations,
+                              const float* W, int Nq, int Ns, int H, int K, int Cin, int Cout,
+                              float extent, int influence, int mode, const float* bn_scale,
+                              const float* bn_shift, const float* bias, float leaky_alpha,
+                              float* out, void* workspace, size_t workspace_bytes,
+                              d3f_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Unary convolution (features @ W) with fused epilogue:
+ *   y = x@W; y = y*bn_scale + bn_shift (opt); y += bias (opt); y += residual[N,Cout] (opt);
+ *   y = LeakyReLU(y) if leaky_alpha >= 0.
+ * ------------------------------------------------------------------------------------------- */
+int d3f_unary_forward(const float* x, const float* W, int N, int Cin, int Cout,
+                      const float* bn_scale, const float* bn_shift, const float* bias,
+                      const float* residual, float leaky_alpha, float* out, d3f_stream_t stream);
+
+/* out[N2,C] = max_h x'[inds[n,h]] with x' = x || colmin(x) (shadow index = N1).
+ * workspace: C floats. */
+size_t d3f_ind_max_pool_workspace_bytes(int C);
+int d3f_ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out,
+                     void* workspace, size_t workspace_bytes, d3f_stream_t stream);
+
+/* out[N2,C] = x'[inds[n,0]] with x' = x || zeros. `ld_inds` = row stride of inds (H). */
+int d3f_closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C,
+                     float* out, d3f_stream_t stream);
+
+/* out[n,:] = x[n,:] * rsqrt(max(sum x^2, eps)) (tf.nn.l2_normalize, models/D3Feat.py:65) */
+int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream);
+
+/* Stand-alone block epilogue for callers that do not use the fused forms
+ * (models/network_blocks.py:149-165 batch_norm inference form, :185-186 leaky_relu, :368 residual add):
+ * y = x*scale[c] + shift[c] (if scale) ; y += residual (if) ; LeakyReLU(leaky_alpha) if >= 0. */
+int d3f_affine_leaky(const float* x, int N, int C, const float* scale, const float* shift,
+                     const float* residual, float leaky_alpha, float* out, d3f_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3FEAT_B200_H_ */

@@ -1,0 +1,81 @@
+"""CPU: host-side logic (workload generator, parameter naming, pyramid radii, oracle pyramid)."""
+import numpy as np
+import pytest
+
+from d3feat_b200 import synth
+from d3feat_b200 import pyramid
+from oracle import native as on
+from oracle import kpconv_np as ok
+
+
+def test_room_fragment_is_seeded_and_exact_size():
+    a = synth.room_fragment(5, 4000)
+    b = synth.room_fragment(5, 4000)
+    assert a.shape == (4000, 3) and a.dtype == np.float32
+    assert np.array_equal(a, b)
+    assert not np.array_equal(a, synth.room_fragment(6, 4000))
+    # voxelised at 0.03: no two points share a cell
+    cells = np.floor(a / 0.03).astype(np.int64)
+    assert np.unique(cells, axis=0).shape[0] == 4000
+
+
+def test_level_radii_follow_tf_descriptor_input():
+    cfg = synth.Config()
+    lv = pyramid._level_radii(cfg)
+    assert len(lv) == 5
+    for l, d in enumerate(lv):
+        assert d["conv_r"] == pytest.approx(0.075 * 2 ** l)
+        if l < 4:
+            assert d["dl"] == pytest.approx(0.06 * 2 ** l)
+            assert d["pool_r"] == pytest.approx(0.075 * 2 ** l)
+            assert d["up_r"] == pytest.approx(0.15 * 2 ** l)
+        else:
+            assert d["dl"] is None
+    cfgd = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.3)
+    lvd = pyramid._level_radii(cfgd)
+    # layer 3 ends with a deformable strided block: pool radius is dl*density (common.py:1361-1364)
+    assert lvd[3]["pool_r"] == pytest.approx(0.75 * 8 * 2)
+    # layer 4 holds a single deformable block: layer_blocks[:-1] is empty, so the radius is NOT doubled
+    # (quirk of common.py:1340 kept as is)
+    assert lvd[4]["conv_r"] == pytest.approx(0.75 * 16)
+
+
+def test_param_names_and_shapes_match_reference_scopes():
+    cfg = synth.Config()
+    p = synth.make_params(cfg, 0)
+    assert p["layer_0/simple_0/weights"].shape == (15, 1, 64)
+    assert p["layer_0/resnetb_1/conv2/weights"].shape == (15, 32, 32)
+    assert p["layer_0/resnetb_1/shortcut/weights"].shape == (64, 128)
+    assert "layer_0/resnetb_strided_2/shortcut/weights" not in p        # dims already match (:604)
+    assert p["layer_1/resnetb_0/conv2/weights"].shape == (15, 64, 64)   # cf. results_kitti layer_1_resnetb_0_conv2.npy
+    assert p["layer_4/resnetb_0/conv2/weights"].shape == (15, 512, 512)
+    assert p["layer_4/resnetb_0/conv3/weights"].shape == (512, 2048)
+    assert p["uplayer_3/unary_0/weights"].shape == (3072, 512)
+    assert p["uplayer_0/last_unary_1/weights"].shape == (64, 32)
+    assert p["layer_2/resnetb_0/conv2/kernel_points"].shape == (15, 3)
+    w = p["layer_1/resnetb_0/conv1/weights"]
+    assert np.allclose(w, np.round(w * 1000) / 1000) and np.abs(w).max() <= 2 * np.sqrt(2 / w.shape[-1]) + 1e-3
+    kp = p["layer_0/simple_0/kernel_points"]
+    assert np.linalg.norm(kp[0]) < 0.01 and np.allclose(np.linalg.norm(kp[1:], axis=1), 1.5 * 0.03, rtol=0.1)
+
+
+def test_oracle_pyramid_and_encoder_shapes():
+    cfg = synth.Config(architecture=synth.ARCH_ENCODER[:6], first_features_dim=16)
+    pts = np.concatenate([synth.room_fragment(0, 1500), synth.room_fragment(1, 1200)], 0)
+    lens = np.array([1500, 1200], np.int32)
+    inputs = ok.descriptor_input_pyramid(cfg, pts, lens, [25, 25, 25], on.port_batch_neighbors,
+                                         on.port_batch_subsampling)
+    assert len(inputs["points"]) == 3
+    assert inputs["neighbors"][0].shape == (2700, 25)
+    assert inputs["pools"][0].shape[0] == inputs["points"][1].shape[0]
+    assert inputs["upsamples"][0].shape[0] == 2700
+    assert inputs["pools"][2].shape == (0, 1)
+    # per-cloud isolation: no neighbour index crosses the cloud boundary
+    nb = inputs["neighbors"][0]
+    assert nb[:1500][nb[:1500] < 2700].max() < 1500 and nb[1500:].min() >= 1500
+    inputs["features"] = np.ones((2700, 1), np.float32)
+    params = synth.make_params(cfg, 1)
+    F = ok.EncoderOracle(cfg, params, np.float32).encoder(inputs)
+    assert [f.shape[1] for f in F] == [32, 64, 128]
+    assert F[2].shape[0] == inputs["points"][2].shape[0]
+    assert all(np.isfinite(f).all() for f in F)
