@@ -17,11 +17,41 @@ Tensors: contiguous CUDA float32 / int32. The kernel points of a KPConv are a re
 variable in the reference (:145-148); here they come from the active ParamStore under
 '<scope>/kernel_points' or, without a store, from the seeded generator in synth.kernel_points.
 """
+import os
+import weakref
+
 import numpy as np
 import torch
 
 from . import _lib
 from . import variables as V
+
+# Tensor-core path: static weights are packed once per weight tensor into the K-major TF32 hi/lo images the
+# tcgen05 kernels consume (d3f_pack_weight). D3F_TENSOR_CORES=0 selects the CUDA-core fp32 kernels instead.
+USE_TENSOR_CORES = os.environ.get("D3F_TENSOR_CORES", "1") != "0"
+_packed_cache = {}     # id(tensor) -> (weakref, version, packed image); entries die with their tensor
+
+
+def packed_weight(w2d_view_of):
+    """Packed image of a weight tensor viewed as [K, N] (unary: [Cin, Cout]; KPConv: [K*Cin, Cout])."""
+    if not USE_TENSOR_CORES:
+        return None
+    w = w2d_view_of
+    # keyed by the tensor OBJECT (weak): the entry dies with the tensor, so a recycled device address can never
+    # alias a stale image; _version catches in-place updates
+    hit = _packed_cache.get(id(w))
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2]
+    K = int(np.prod(w.shape[:-1]))
+    N = int(w.shape[-1])
+    L = _lib.lib()
+    packed = torch.empty((L.d3f_packed_weight_floats(K, N),), dtype=torch.float32, device=w.device)
+    _lib.check(L.d3f_pack_weight(_lib.ptr(w), K, N, _lib.ptr(packed), _lib.stream()), "d3f_pack_weight")
+    if hit is None or hit[0]() is not w:
+        weakref.finalize(w, _packed_cache.pop, id(w), None)
+    _packed_cache[id(w)] = (weakref.ref(w), w._version, packed)
+    return packed
+
 
 _INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
 _MODE = {"sum": 0, "closest": 1}
@@ -44,7 +74,7 @@ def unary_convolution(features, K_values, *, epilogue=None, residual=None):
         raise ValueError("unary_convolution: features %s do not match K_values %s" % (tuple(x.shape), tuple(w.shape)))
     scale, shift, alpha = _epilogue_args(epilogue)
     out = torch.empty((N, Cout), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().d3f_unary_forward(_lib.ptr(x), _lib.ptr(w), N, Cin, Cout, _lib.ptr(scale), _lib.ptr(shift),
+    _lib.check(_lib.lib().d3f_unary_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(packed_weight(w)), N, Cin, Cout, _lib.ptr(scale), _lib.ptr(shift),
                                             None, _lib.ptr(residual.contiguous()) if residual is not None else None,
                                             alpha, _lib.ptr(out), _lib.stream()), "d3f_unary_forward")
     return out
@@ -74,7 +104,7 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
     ws = _lib.workspace(L.d3f_kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout), q.device)
     out = torch.empty((Nq, Cout), dtype=torch.float32, device=q.device)
     _lib.check(L.d3f_kpconv_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp), _lib.ptr(W),
-                                    Nq, Ns, H, K, Cin, Cout, float(KP_extent), _INFLUENCE[KP_influence],
+                                    _lib.ptr(packed_weight(W)), Nq, Ns, H, K, Cin, Cout, float(KP_extent), _INFLUENCE[KP_influence],
                                     _MODE[aggregation_mode], 1, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(bias),
                                     alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()),
                "d3f_kpconv_forward")
@@ -96,7 +126,7 @@ def KPConv_deform_ops(query_points, support_points, neighbors_indices, features,
     ws = _lib.workspace(L.d3f_kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout), q.device)
     out = torch.empty((Nq, Cout), dtype=torch.float32, device=q.device)
     _lib.check(L.d3f_kpconv_deform_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp),
-                                           _lib.ptr(off), _lib.ptr(mod), _lib.ptr(W), Nq, Ns, H, K, Cin, Cout,
+                                           _lib.ptr(off), _lib.ptr(mod), _lib.ptr(W), _lib.ptr(packed_weight(W)), Nq, Ns, H, K, Cin, Cout,
                                            float(KP_extent), _INFLUENCE[KP_influence], _MODE[mode], _lib.ptr(scale),
                                            _lib.ptr(shift), None, alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                                            _lib.stream()), "d3f_kpconv_deform_forward")

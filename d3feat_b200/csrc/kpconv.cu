@@ -195,16 +195,266 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Para
   if (p.inv_nn != nullptr && lane == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Stage 1, packed-FMA version (the one the encoder's layers use). Blackwell reaches its full fp32 rate only
+// through FFMA2 (fma.rn.f32x2): the K = 15 kernel points are padded to 16 and handled as 8 PAIRS, so one
+// FFMA2 updates (wf[2j], wf[2j+1]) of a channel: 8 FFMA2 per neighbour and channel instead of 15 FFMA, fed by
+// four broadcast LDS.128 that deliver the pairs already packed. For Cin = 32 a warp serves TWO queries (one
+// per half-warp, 2 channels per lane) so that the weight reads and the row loads are amortised over both.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+// MUFU.SQRT: one instruction instead of the ~10-instruction IEEE sequence (max error ~1 ulp; tolerance 1e-4)
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <int CPL, int QPW, bool DEFORM>
+__global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1_v2_kernel(Stage1Params p) {
+  constexpr int K = 15, KP = 16;
+  constexpr int LPQ = 32 / QPW;  // lanes (= neighbour slots per pass) per query
+  static_assert(CPL == 2 || CPL == 4, "channels per lane");
+  __shared__ __align__(16) float wts[kS1Warps][32 * kWStride];
+  __shared__ float kp_s[kS1Warps][QPW][KP * 3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPQ, sl = lane % LPQ;
+  const int nfirst = p.n0 + (blockIdx.x * kS1Warps + warp) * QPW;
+  if (nfirst >= p.n1) return;  // warp-uniform
+  const int n = nfirst + sub;
+  const bool qvalid = n < p.n1;
+  const int nq = qvalid ? n : nfirst;  // invalid half-warps shadow the first query (results discarded)
+
+  for (int t = sl; t < KP * 3; t += LPQ) {
+    float v = t < K * 3 ? p.Kp[t] : 0.f;
+    if (DEFORM && t < K * 3) v += p.offsets[(size_t)nq * K * 3 + t];
+    kp_s[warp][sub][t] = v;
+  }
+  const float qx = p.q[3 * (size_t)nq], qy = p.q[3 * (size_t)nq + 1], qz = p.q[3 * (size_t)nq + 2];
+  const int* row = p.idx + (size_t)nq * p.H;
+  const float ext2 = p.extent * p.extent;
+  const unsigned gshift = (unsigned)(sub * LPQ);
+  const unsigned gmask = LPQ == 32 ? 0xffffffffu : 0xffffu;
+  float* wq = &wts[warp][sub * LPQ * kWStride];
+  __syncwarp();
+
+  int nn_count = 0;
+  constexpr int c_step = LPQ * CPL;
+  for (int c0 = 0; c0 < p.Cin; c0 += c_step) {
+    float2 acc[KP / 2][CPL];
+#pragma unroll
+    for (int j = 0; j < KP / 2; ++j)
+#pragma unroll
+      for (int v = 0; v < CPL; ++v) acc[j][v] = make_float2(0.f, 0.f);
+    const int c = c0 + sl * CPL;   // Cin is a multiple of c_step for every instantiation dispatched here
+
+    for (int h0 = 0; h0 < p.H; h0 += LPQ) {
+      // ---- phase A: lane <-> neighbour h0+sl of this lane's query ---------------------------------------
+      const int h = h0 + sl;
+      int id = (h < p.H) ? row[h] : p.Ns;
+      if (id < 0 || id > p.Ns) id = p.Ns;
+      const bool real = id < p.Ns;
+      float rx, ry, rz;
+      if (real) {
+        rx = p.s[3 * (size_t)id] - qx; ry = p.s[3 * (size_t)id + 1] - qy; rz = p.s[3 * (size_t)id + 2] - qz;
+      } else {
+        rx = p.shadow - qx; ry = p.shadow - qy; rz = p.shadow - qz;
+      }
+      float w[KP];
+      float dmin = 3.0e38f;
+      int kmin = 0;
+      bool in_range = false;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float dx = rx - kp_s[warp][sub][3 * k], dy = ry - kp_s[warp][sub][3 * k + 1], dz = rz - kp_s[warp][sub][3 * k + 2];
+        float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < dmin) { dmin = d2; kmin = k; }
+        in_range = in_range || (d2 < ext2);
+        float wk;
+        if (p.influence == D3F_INFLUENCE_LINEAR) wk = fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
+        else if (p.influence == D3F_INFLUENCE_GAUSSIAN) wk = __expf(-d2 * p.gauss_inv);
+        else wk = DEFORM ? (d2 < ext2 ? 1.f : 0.f) : 1.f;
+        w[k] = wk;
+      }
+      w[K] = 0.f;
+      if (p.closest) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = (k == kmin) ? w[k] : 0.f;
+      }
+      const bool keep = real && qvalid && (!DEFORM || in_range);
+#pragma unroll
+      for (int kq = 0; kq < KP / 4; ++kq)
+        *reinterpret_cast<float4*>(&wq[sl * kWStride + 4 * kq]) =
+            keep ? make_float4(w[4 * kq], w[4 * kq + 1], w[4 * kq + 2], w[4 * kq + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 == 0 && p.flag != nullptr) {
+        bool cnt = real && p.flag[id] != 0;
+        nn_count += __popc((__ballot_sync(0xffffffffu, cnt) >> gshift) & gmask);
+      }
+      unsigned m = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
+      int cnt = __popc(m);
+      if (QPW == 2) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
+      __syncwarp();
+
+      // ---- phase B: both half-warps walk their kept neighbours in lockstep, kUnroll per step: all row loads
+      //      of a step are issued before the first FMA consumes one (memory-level parallelism) -------------
+      constexpr int kUnroll = CPL == 4 ? 2 : 4;
+      for (int it = 0; it < cnt; it += kUnroll) {
+        int hh[kUnroll];
+        float f[kUnroll][CPL];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          const bool act = m != 0;
+          hh[u] = act ? __ffs(m) - 1 : 0;
+          m &= m - 1;
+          const int idh = __shfl_sync(0xffffffffu, id, (int)gshift + hh[u]);
+          const float* fp = p.feat + (size_t)idh * p.Cin + c;
+          if (CPL == 4) {
+            float4 t = act ? __ldg(reinterpret_cast<const float4*>(fp)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            f[u][0] = t.x; f[u][1] = t.y; f[u][2 % CPL] = t.z; f[u][3 % CPL] = t.w;
+          } else {
+            float2 t = act ? __ldg(reinterpret_cast<const float2*>(fp)) : make_float2(0.f, 0.f);
+            f[u][0] = t.x; f[u][1] = t.y;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+          // an inactive slot reads slot 0's weights with f = 0: contributes nothing
+          const float4* wp = reinterpret_cast<const float4*>(&wq[hh[u] * kWStride]);
+          float2 wpair[KP / 2];
+#pragma unroll
+          for (int kq = 0; kq < KP / 4; ++kq) {
+            float4 t = wp[kq];
+            wpair[2 * kq] = make_float2(t.x, t.y);
+            wpair[2 * kq + 1] = make_float2(t.z, t.w);
+          }
+#pragma unroll
+          for (int v = 0; v < CPL; ++v) {
+            const float2 fd = make_float2(f[u][v], f[u][v]);
+#pragma unroll
+            for (int j = 0; j < KP / 2; ++j) acc[j][v] = ffma2(wpair[j], fd, acc[j][v]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- write wf[n, k, c .. c+CPL) (optionally modulated, :489-490) ------------------------------------
+    if (qvalid) {
+      float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)n * K + k] : 1.f;
+        float o[CPL];
+#pragma unroll
+        for (int v = 0; v < CPL; ++v) o[v] = ((k & 1) ? acc[k / 2][v].y : acc[k / 2][v].x) * mod;
+        if (CPL == 4) *reinterpret_cast<float4*>(dst + (size_t)k * p.Cin) = make_float4(o[0], o[1], o[2 % CPL], o[3 % CPL]);
+        else *reinterpret_cast<float2*>(dst + (size_t)k * p.Cin) = make_float2(o[0], o[1]);
+      }
+    }
+  }
+  if (p.inv_nn != nullptr && qvalid && sl == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
+}
+
 template <int K, bool DEFORM>
 static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
   int nq = p.n1 - p.n0;
-  int blocks = ceil_div(nq, kS1Warps);
   bool al16 = (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.wf) & 15) == 0;
-  if (p.Cin % 128 == 0 && al16) kpconv_stage1_kernel<K, 4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-  else if (p.Cin % 64 == 0 && al16) kpconv_stage1_kernel<K, 2, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-  else kpconv_stage1_kernel<K, 1, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+  if (K == 15 && al16 && p.Cin % 128 == 0) {
+    kpconv_stage1_v2_kernel<4, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
+  } else if (K == 15 && al16 && p.Cin % 64 == 0) {
+    kpconv_stage1_v2_kernel<2, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
+  } else if (K == 15 && al16 && p.Cin % 32 == 0) {
+    kpconv_stage1_v2_kernel<2, 2, DEFORM><<<ceil_div(nq, kS1Warps * 2), kS1Warps * 32, 0, stream>>>(p);
+  } else {
+    // generic path (first layer Cin = 1, odd widths)
+    kpconv_stage1_kernel<K, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
+  }
   D3F_LAUNCH_CHECK("kpconv_stage1_kernel");
   return D3F_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// First layer of the network: Cin = 1 (constant-one input feature, datasets/ThreeDMatch.py:316). The whole
+// KPConv of a query fits in one warp: lanes <-> neighbours for the correlation weights, a warp reduction gives
+// wf[k] = sum_h w[h,k] f[h], then lanes <-> output channels for out[c] = (sum_k wf[k] W[k,0,c]) / nn + epilogue.
+// One kernel, nothing but the output row is written.
+struct Cin1Params {
+  const float* q; const float* s; const int* idx; const float* feat; const float* Kp; const float* W;
+  int Nq, Ns, H, Cout;
+  float inv_scale, gauss_inv;
+  int influence, closest, normalize;
+  float shadow;
+  const float* bn_scale; const float* bn_shift; const float* bias;
+  float leaky_alpha;
+  float* out;
+};
+
+__global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
+  constexpr int K = 15;
+  __shared__ float kp_s[K * 3];
+  for (int t = threadIdx.x; t < K * 3; t += blockDim.x) kp_s[t] = p.Kp[t];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= p.Nq) return;
+  const float qx = p.q[3 * (size_t)n], qy = p.q[3 * (size_t)n + 1], qz = p.q[3 * (size_t)n + 2];
+  const int* row = p.idx + (size_t)n * p.H;
+  float wf[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) wf[k] = 0.f;
+  int nn = 0;
+  for (int h0 = 0; h0 < p.H; h0 += 32) {
+    const int h = h0 + lane;
+    int id = (h < p.H) ? row[h] : p.Ns;
+    if (id < 0 || id > p.Ns) id = p.Ns;
+    const bool real = id < p.Ns;
+    float f = 0.f, rx = p.shadow - qx, ry = p.shadow - qy, rz = p.shadow - qz;
+    if (real) {
+      f = p.feat[id];
+      rx = p.s[3 * (size_t)id] - qx; ry = p.s[3 * (size_t)id + 1] - qy; rz = p.s[3 * (size_t)id + 2] - qz;
+    }
+    nn += __popc(__ballot_sync(0xffffffffu, real && f > 0.f));
+    float w[K];
+    float dmin = 3.0e38f;
+    int kmin = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float dx = rx - kp_s[3 * k], dy = ry - kp_s[3 * k + 1], dz = rz - kp_s[3 * k + 2];
+      float d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < dmin) { dmin = d2; kmin = k; }
+      float wk;
+      if (p.influence == D3F_INFLUENCE_LINEAR) wk = fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
+      else if (p.influence == D3F_INFLUENCE_GAUSSIAN) wk = __expf(-d2 * p.gauss_inv);
+      else wk = 1.f;
+      w[k] = wk;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float t = (p.closest && k != kmin) ? 0.f : w[k] * f;   // f = 0 for shadow neighbours
+      wf[k] += t;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wf[k] += __shfl_xor_sync(0xffffffffu, wf[k], o);
+  }
+  const float inv_nn = p.normalize ? 1.f / (float)max(nn, 1) : 1.f;
+  for (int c = lane; c < p.Cout; c += 32) {
+    float y = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) y = fmaf(wf[k], __ldg(p.W + (size_t)k * p.Cout + c), y);
+    y *= inv_nn;
+    if (p.bn_scale) y = fmaf(y, p.bn_scale[c], p.bn_shift[c]);
+    if (p.bias) y += p.bias[c];
+    if (p.leaky_alpha >= 0.f) y = y > 0.f ? y : y * p.leaky_alpha;
+    p.out[(size_t)n * p.Cout + c] = y;
+  }
 }
 
 // queries per chunk: keep the wf chunk (K*Cin floats per query) around 48 MB so it is produced and
@@ -229,8 +479,9 @@ size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
 }
 
 int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* idx, const float* feat,
-                        const float* Kp, const float* offsets, const float* modulations, const float* W, int Nq,
-                        int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, int normalize,
+                        const float* Kp, const float* offsets, const float* modulations, const float* W,
+                        const float* W_packed, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent,
+                        int influence, int mode, int normalize,
                         const float* bn_scale, const float* bn_shift, const float* bias, float leaky_alpha,
                         float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   D3F_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 0 && Cin >= 1 && Cout >= 1, D3F_ERR_INVALID,
@@ -253,6 +504,21 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   float* inv_nn = cv.take<float>(chunk);
   unsigned char* flag = cv.take<unsigned char>(Ns + 1);
 
+  if (Cin == 1 && !deform) {
+    Cin1Params c1;
+    c1.q = q; c1.s = s; c1.idx = idx; c1.feat = feat; c1.Kp = Kp; c1.W = W;
+    c1.Nq = Nq; c1.Ns = Ns; c1.H = H; c1.Cout = Cout;
+    c1.inv_scale = 1.f / (2.f * extent);
+    float sg = extent * 0.3f;
+    c1.gauss_inv = 1.f / (2.f * sg * sg + 1e-9f);
+    c1.influence = influence; c1.closest = mode == D3F_MODE_CLOSEST; c1.normalize = normalize != 0;
+    c1.shadow = 1e6f;
+    c1.bn_scale = bn_scale; c1.bn_shift = bn_shift; c1.bias = bias; c1.leaky_alpha = leaky_alpha;
+    c1.out = out;
+    kpconv_cin1_kernel<<<ceil_div(Nq * 32, 256), 256, 0, stream>>>(c1);
+    D3F_LAUNCH_CHECK("kpconv_cin1_kernel");
+    return D3F_OK;
+  }
   const bool norm = normalize != 0 && !deform;
   if (norm && Ns > 0) {
     rowsum_flag_kernel<<<ceil_div(Ns * 32, 256), 256, 0, stream>>>(feat, Ns, Cin, flag);
@@ -280,7 +546,10 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     ep.rowscale = norm ? inv_nn : nullptr;
     ep.bn_scale = bn_scale; ep.bn_shift = bn_shift; ep.bias = bias; ep.residual = nullptr;
     ep.leaky_alpha = leaky_alpha;
-    rc = gemm_f32(wf, W, out + (size_t)n0 * Cout, p.n1 - n0, Cout, K * Cin, ep, stream);
+    if (W_packed != nullptr && tc_gemm_supported(wf, K * Cin))
+      rc = tc_gemm(wf, W_packed, out + (size_t)n0 * Cout, p.n1 - n0, Cout, K * Cin, ep, stream);
+    else
+      rc = gemm_f32(wf, W, out + (size_t)n0 * Cout, p.n1 - n0, Cout, K * Cin, ep, stream);
     if (rc) return rc;
   }
   return D3F_OK;

@@ -15,6 +15,12 @@ struct Epilogue {
 };
 int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
 
+// ---- tc_gemm.cu (tcgen05 / TMEM, 3xTF32) ------------------------------------------------------------
+size_t tc_packed_floats(int K, int N);
+int tc_pack_weight(const float* W, int K, int N, float* packed, cudaStream_t stream);
+bool tc_gemm_supported(const float* A, int K);
+int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
+
 // ---- grid.cu ----------------------------------------------------------------------------------------
 int launch_batch_start(const int* len, int B, int* start, cudaStream_t stream);
 int bbox_device(const float* pts, int N, float* out_bbox, cudaStream_t stream);
@@ -38,7 +44,8 @@ int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, 
 // ---- kpconv.cu --------------------------------------------------------------------------------------
 size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
 int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* idx, const float* feat,
-                        const float* Kp, const float* offsets, const float* modulations, const float* W, int Nq,
+                        const float* Kp, const float* offsets, const float* modulations, const float* W,
+                        const float* W_packed, int Nq,
                         int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, int normalize,
                         const float* bn_scale, const float* bn_shift, const float* bias, float leaky_alpha,
                         float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);

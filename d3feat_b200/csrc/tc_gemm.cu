@@ -1,0 +1,362 @@
+// Tensor-core GEMM for sm_100a: tcgen05.mma (kind::tf32) with the accumulator in TMEM, fp32-accurate through
+// a 3xTF32 split:   A = Ah + Al,  B = Bh + Bl  (Ah/Bh = operand rounded to TF32, Al/Bl = exact remainder)
+//                   D += Ah*Bh + Al*Bh + Ah*Bl          (dropped Al*Bl term ~ 2^-22 relative)
+//
+//   C[M,N] = epilogue( rowscale[m] * (A[M,K] @ W[K,N]) )
+//
+// * A is the activation matrix (row-major fp32 in global memory). It is loaded by 4 producer warps with coalesced
+//   128-bit loads, split into (hi, lo) in registers and written to shared memory in the canonical K-major
+//   SWIZZLE_128B layout the UMMA descriptor expects (rows of 128 B = 32 fp32, 16-byte chunks XOR-ed with row%8).
+// * W is static: it is packed once (pack_weight_kernel) into K-major [Npad, Kpad] hi/lo images.
+// * One elected thread of warp 4 issues the MMAs (M = 128, N = BN, K = 8 per instruction); a 3-stage
+//   mbarrier ring overlaps the producers with the tensor pipe; tcgen05.commit releases stages / signals the epilogue.
+// * Epilogue: warps 0-3 read their 32 TMEM lanes (tcgen05.ld 32x32b), apply rowscale / BN / bias / residual /
+//   LeakyReLU and store rows straight to global memory.
+#include "ops.cuh"
+
+namespace d3f {
+
+constexpr int kTcBM = 128;       // rows per CTA (UMMA M)
+constexpr int kTcBK = 32;        // fp32 per k-chunk = one 128 B swizzle row
+constexpr int kTcStages = 2;   // 2 x (40..64 KB): two CTAs per SM for BN <= 64 overlap each other's phases
+constexpr int kTcProducerThreads = 128;
+constexpr int kTcThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
+//   [0,14) start>>4, [16,30) LBO>>4 (=1, unused for swizzled K-major), [32,46) SBO>>4 (8 rows * 128 B = 1024 B),
+//   [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N>>3, M>>4
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// round-to-nearest TF32 split: hi has 10 explicit mantissa bits, lo = x - hi exactly
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// W[K,N] row-major -> packed[2][Npad][Kpad] (hi image, then lo image), K-major, zero padded.
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ W, int K, int N, int Kpad,
+                                                          int Npad, float* __restrict__ packed) {
+  long long total = (long long)Npad * Kpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int n = (int)(i / Kpad), k = (int)(i % Kpad);
+    float x = (n < N && k < K) ? W[(size_t)k * N + n] : 0.f;
+    float hi, lo;
+    split_tf32(x, hi, lo);
+    packed[i] = hi;
+    packed[total + i] = lo;
+  }
+}
+
+int tc_padded_k(int K) { return (K + kTcBK - 1) / kTcBK * kTcBK; }
+int tc_block_n(int N) { return N > 64 ? 128 : (N > 32 ? 64 : 32); }
+int tc_padded_n(int N) { int bn = tc_block_n(N); return (N + bn - 1) / bn * bn; }
+size_t tc_packed_floats(int K, int N) { return 2 * (size_t)tc_padded_k(K) * tc_padded_n(N); }
+
+int tc_pack_weight(const float* W, int K, int N, float* packed, cudaStream_t stream) {
+  D3F_REQUIRE(K >= 1 && N >= 1 && W && packed, D3F_ERR_INVALID, "pack_weight: bad arguments");
+  int Kpad = tc_padded_k(K), Npad = tc_padded_n(N);
+  long long total = (long long)Npad * Kpad;
+  int blocks = (int)min((total + 255) / 256, (long long)kNumSMs * 8);
+  pack_weight_kernel<<<blocks, 256, 0, stream>>>(W, K, N, Kpad, Npad, packed);
+  D3F_LAUNCH_CHECK("pack_weight_kernel");
+  return D3F_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The tensor pipe truncates (round-toward-zero) when it writes the fp32 accumulator back to TMEM: measured bias
+// ~ -1.1e-8 * K relative for all-positive data (scripts/tc_accuracy_probe.py). The k-chunks are therefore
+// rotated over kAcc independent TMEM accumulators (2 x 128 or 4 x 64 / 4 x 32 columns) that the epilogue adds
+// in registers with round-to-nearest: the truncation chain per accumulator is kAcc times shorter.
+template <int BN>
+struct TcAcc {
+  static constexpr int kAcc = BN >= 128 ? 2 : 4;   // <= 256 TMEM columns per CTA: two CTAs fit in the 512 columns
+  static constexpr int kCols = kAcc * BN;   // power of two <= 512
+};
+
+template <int BN>
+struct TcSmem {
+  static constexpr int kABytes = kTcBM * 128;  // one image (hi or lo) of the A tile
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kTotal = kTcStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, BN >= 128 ? 1 : 2)
+tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ C, int M, int N, int K,
+               int Kpad, int Npad, Epilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  using S = TcSmem<BN>;
+  // 1024 B alignment: SWIZZLE_128B atoms are 8 rows x 128 B and the swizzle uses absolute address bits
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + kTcStages * S::kStageBytes);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kTcStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
+  const int nk = Kpad / kTcBK;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTcStages; ++s) {
+      mbar_init(smem_u32(&bars[s]), kTcProducerThreads);
+      mbar_init(smem_u32(&bars[kTcStages + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * kTcStages]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TcAcc<BN>::kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers: global -> registers -> (hi, lo) -> swizzled shared memory ==========
+    const int chunk = tid & 7;      // 16-byte chunk inside the 128-byte row
+    const int rsub = tid >> 3;      // 0..15: row inside a 16-row slab
+    const float* Bhi = Bp;
+    const float* Blo = Bp + (size_t)Npad * Kpad;
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % kTcStages;
+      const uint32_t ph = (uint32_t)(kt / kTcStages) & 1u;
+      mbar_wait(smem_u32(&bars[kTcStages + s]), ph ^ 1u);
+      uint8_t* st = smem + s * S::kStageBytes;
+      const int k0 = kt * kTcBK + chunk * 4;
+      // ---- A tile: 128 rows, 8 slabs of 16 rows
+      float4 a[kTcBM / 16];
+#pragma unroll
+      for (int it = 0; it < kTcBM / 16; ++it) {
+        int row = it * 16 + rsub;
+        int gm = m0 + row;
+        a[it] = (gm < M && k0 < K) ? *reinterpret_cast<const float4*>(A + (size_t)gm * K + k0)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // ---- B tiles (already split): BN rows
+      float4 bh[BN / 16], bl[BN / 16];
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {
+        int row = it * 16 + rsub;
+        size_t off = (size_t)(n0 + row) * Kpad + k0;
+        bh[it] = *reinterpret_cast<const float4*>(Bhi + off);
+        bl[it] = *reinterpret_cast<const float4*>(Blo + off);
+      }
+#pragma unroll
+      for (int it = 0; it < kTcBM / 16; ++it) {
+        int row = it * 16 + rsub;
+        uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        float4 hi, lo;
+        split_tf32(a[it].x, hi.x, lo.x);
+        split_tf32(a[it].y, hi.y, lo.y);
+        split_tf32(a[it].z, hi.z, lo.z);
+        split_tf32(a[it].w, hi.w, lo.w);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + S::kABytes + off) = lo;
+      }
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {
+        int row = it * 16 + rsub;
+        uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        *reinterpret_cast<float4*>(st + 2 * S::kABytes + off) = bh[it];
+        *reinterpret_cast<float4*>(st + 2 * S::kABytes + S::kBBytes + off) = bl[it];
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&bars[s]));
+    }
+
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global ============
+    // Each warp owns TMEM lanes / tile rows [32w, 32w+32). A thread reads its row's 32 columns from TMEM, the
+    // warp transposes them through a padded 32x33 shared tile (the stage buffers are free: every MMA that
+    // read them has retired when the accumulator barrier fires), then lane <-> column: the per-column BN /
+    // bias parameters sit in registers and every residual load / store is one coalesced 128-byte row segment.
+    mbar_wait(smem_u32(&bars[2 * kTcStages]), 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;      // TMEM lane == tile row; warp w may only touch lanes [32w, 32w+32)
+    const int gm = m0 + row;
+    const float rs = (ep.rowscale != nullptr && gm < M) ? ep.rowscale[gm] : 1.f;
+    const int nacc = nk < TcAcc<BN>::kAcc ? nk : TcAcc<BN>::kAcc;
+    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    const int rows_here = min(32, M - (m0 + warp * 32));   // rows of this warp that exist (<= 0: none)
+    const bool has_bn = ep.bn_scale != nullptr, has_bias = ep.bias != nullptr, has_res = ep.residual != nullptr;
+    const bool has_leaky = ep.leaky_alpha >= 0.f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      const int gn = n0 + c0 + lane;
+      const bool col_ok = gn < N;
+      const size_t base = (size_t)(m0 + warp * 32) * N + gn;
+      // residual rows of this column chunk: all 32 coalesced loads are in flight before anything waits on them
+      float res[32];
+      if (has_res) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) res[rr] = (col_ok && rr < rows_here) ? ep.residual[base + (size_t)rr * N] : 0.f;
+      }
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll 1
+      for (int a = 1; a < nacc; ++a) {
+        float w[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0), w);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j] * rs;
+      __syncwarp();
+      const float sc = (has_bn && col_ok) ? ep.bn_scale[gn] : 1.f;
+      const float sh = (has_bn && col_ok) ? ep.bn_shift[gn] : 0.f;
+      const float bi = (has_bias && col_ok) ? ep.bias[gn] : 0.f;
+      if (col_ok) {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          if (rr < rows_here) {
+            float y = fmaf(tile[rr * 33 + lane], sc, sh) + bi;
+            if (has_res) y += res[rr];
+            if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
+            C[base + (size_t)rr * N] = y;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  } else {
+    // ===================== MMA issuer (warp 4, one elected lane) ========================================
+    const uint32_t idesc = make_idesc_tf32(kTcBM, BN);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % kTcStages;
+      const uint32_t ph = (uint32_t)(kt / kTcStages) & 1u;
+      mbar_wait(smem_u32(&bars[s]), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+        const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + S::kABytes);
+        const uint64_t b_hi = make_smem_desc(sa + 2 * S::kABytes), b_lo = make_smem_desc(sa + 2 * S::kABytes + S::kBBytes);
+#pragma unroll
+        for (int j = 0; j < kTcBK / 8; ++j) {
+          const uint64_t adv = (uint64_t)((j * 32) >> 4);   // +32 B per K = 8 step inside the swizzle atom
+          const uint32_t d = tmem_base + (uint32_t)((kt % TcAcc<BN>::kAcc) * BN);
+          umma_tf32(d, a_hi + adv, b_hi + adv, idesc, (kt >= TcAcc<BN>::kAcc || j != 0) ? 1u : 0u);
+          umma_tf32(d, a_lo + adv, b_hi + adv, idesc, 1u);
+          umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
+        }
+        umma_commit(smem_u32(&bars[kTcStages + s]));                 // stage free once these MMAs retire
+        if (kt == nk - 1) umma_commit(smem_u32(&bars[2 * kTcStages]));  // accumulator complete
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)TcAcc<BN>::kCols)
+                 : "memory");
+  }
+}
+
+template <int BN>
+static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
+                     cudaStream_t stream) {
+  using S = TcSmem<BN>;
+  static bool configured = false;   // idempotent attribute set; benign if two host threads race
+  if (!configured) {
+    D3F_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  int Kpad = tc_padded_k(K), Npad = tc_padded_n(N);
+  dim3 grid(Npad / BN, ceil_div(M, kTcBM));
+  tc_gemm_kernel<BN><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, C, M, N, K, Kpad, Npad, ep);
+  D3F_LAUNCH_CHECK("tc_gemm_kernel");
+  return D3F_OK;
+}
+
+bool tc_gemm_supported(const float* A, int K) {
+  return (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+}
+
+// A[M,K] fp32 row-major, Bp = packed weight (tc_pack_weight), C[M,N]
+int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return D3F_OK;
+  D3F_REQUIRE(tc_gemm_supported(A, K), D3F_ERR_INVALID, "tc_gemm: needs K %% 4 == 0 and 16-byte aligned A");
+  switch (tc_block_n(N)) {
+    case 128: return launch_tc<128>(A, Bp, C, M, N, K, ep, stream);
+    case 64: return launch_tc<64>(A, Bp, C, M, N, K, ep, stream);
+    default: return launch_tc<32>(A, Bp, C, M, N, K, ep, stream);
+  }
+}
+
+}  // namespace d3f

@@ -110,6 +110,16 @@ int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int 
                               int pad_value, int* out_idx, d3f_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Static weights for the tensor-core path. A weight matrix W[K,N] (row-major; for KPConv the [K*Cin, Cout]
+ * view of K_values[K,Cin,Cout]) is packed ONCE into the K-major TF32 hi/lo images the tcgen05 kernels
+ * consume (3xTF32 split: fp32-level accuracy on the 5th-gen tensor cores). Every forward entry point takes
+ * the packed image as an optional `W_packed` argument: NULL selects the CUDA-core fp32 path (same results
+ * within rounding), non-NULL the tcgen05 path.
+ * ------------------------------------------------------------------------------------------- */
+size_t d3f_packed_weight_floats(int K, int N);
+int d3f_pack_weight(const float* W, int K, int N, float* packed, d3f_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Rigid KPConv forward (KPConv_ops, convolution_ops.py:161-255), fused with the block epilogue.
  *   q[Nq,3], s[Ns,3], idx[Nq,H] (shadow index = Ns), feat[Ns,Cin], Kp[K,3], W[K,Cin,Cout].
  *   out[Nq,Cout] = epilogue( (sum_k (sum_h w[n,h,k] feat[idx[n,h]]) W_k) / nn[n] )
@@ -121,7 +131,8 @@ int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int 
  * ------------------------------------------------------------------------------------------- */
 size_t d3f_kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
 int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const float* feat,
-                       const float* Kp, const float* W, int Nq, int Ns, int H, int K, int Cin,
+                       const float* Kp, const float* W, const float* W_packed, int Nq, int Ns, int H,
+                       int K, int Cin,
                        int Cout, float extent, int influence, int mode, int normalize,
                        const float* bn_scale, const float* bn_shift, const float* bias,
                        float leaky_alpha, float* out, void* workspace, size_t workspace_bytes,
@@ -132,7 +143,8 @@ int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const flo
  * point are dropped (:435-451); optional modulations[n,K]; no neighbour-count normalisation. */
 int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, const float* feat,
                               const float* Kp, const float* offsets, const float* modulations,
-                              const float* W, int Nq, int Ns, int H, int K, int Cin, int Cout,
+                              const float* W, const float* W_packed, int Nq, int Ns, int H, int K,
+                              int Cin, int Cout,
                               float extent, int influence, int mode, const float* bn_scale,
                               const float* bn_shift, const float* bias, float leaky_alpha,
                               float* out, void* workspace, size_t workspace_bytes,
@@ -143,7 +155,7 @@ int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, co
  *   y = x@W; y = y*bn_scale + bn_shift (opt); y += bias (opt); y += residual[N,Cout] (opt);
  *   y = LeakyReLU(y) if leaky_alpha >= 0.
  * ------------------------------------------------------------------------------------------- */
-int d3f_unary_forward(const float* x, const float* W, int N, int Cin, int Cout,
+int d3f_unary_forward(const float* x, const float* W, const float* W_packed, int N, int Cin, int Cout,
                       const float* bn_scale, const float* bn_shift, const float* bias,
                       const float* residual, float leaky_alpha, float* out, d3f_stream_t stream);
 
