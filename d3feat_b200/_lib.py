@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libd3feat_b200.so")
+# D3F_LIB: alternative build of the same library (kernel-tuning experiments); never a different backend
+LIB_PATH = os.environ.get("D3F_LIB") or os.path.join(_HERE, "libd3feat_b200.so")
 
 # every symbol include/d3feat_b200.h declares: (name, restype, argtypes)
 _P, _I, _F, _Z, _LL = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
@@ -28,9 +29,10 @@ SYMBOLS = [
     ("d3f_kpconv_workspace_bytes", _Z, [_I, _I, _I, _I, _I, _I]),
     ("d3f_packed_weight_floats", _Z, [_I, _I]),
     ("d3f_pack_weight", _I, [_P, _I, _I, _P, _P]),
-    ("d3f_kpconv_forward", _I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P, _P, _P, _F, _P,
+    ("d3f_radius_neighbors_order", _I, [_P, _I, _I, _F, _P, _P, _P]),
+    ("d3f_kpconv_forward", _I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P, _P, _P, _F, _P,
                                 _P, _Z, _P]),
-    ("d3f_kpconv_deform_forward", _I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
+    ("d3f_kpconv_deform_forward", _I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
                                        _P, _F, _P, _P, _Z, _P]),
     ("d3f_unary_forward", _I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
     ("d3f_ind_max_pool_workspace_bytes", _Z, [_I]),

@@ -88,8 +88,10 @@ def _check_enums(KP_influence, aggregation_mode):
 
 
 def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
-               KP_influence, aggregation_mode, *, epilogue=None, bias=None):
-    """Rigid KPConv (:161-255): one fused launch sequence, no [N,H,K,*] intermediates."""
+               KP_influence, aggregation_mode, *, epilogue=None, bias=None, query_order=None):
+    """Rigid KPConv (:161-255): one fused launch sequence, no [N,H,K,*] intermediates.
+    query_order (extension): int32[Nq] visiting order of the queries (hash-grid cell order from the pyramid);
+    a pure scheduling hint -- every query still writes its own output row."""
     _check_enums(KP_influence, aggregation_mode)
     q, s = query_points.contiguous(), support_points.contiguous()
     idx, f = neighbors_indices.contiguous(), features.contiguous()
@@ -104,7 +106,7 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
     ws = _lib.workspace(L.d3f_kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout), q.device)
     out = torch.empty((Nq, Cout), dtype=torch.float32, device=q.device)
     _lib.check(L.d3f_kpconv_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp), _lib.ptr(W),
-                                    _lib.ptr(packed_weight(W)), Nq, Ns, H, K, Cin, Cout, float(KP_extent), _INFLUENCE[KP_influence],
+                                    _lib.ptr(packed_weight(W)), _lib.ptr(query_order), Nq, Ns, H, K, Cin, Cout, float(KP_extent), _INFLUENCE[KP_influence],
                                     _MODE[aggregation_mode], 1, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(bias),
                                     alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()),
                "d3f_kpconv_forward")
@@ -112,7 +114,7 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
 
 
 def KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations,
-                      K_values, KP_extent, KP_influence, mode, *, epilogue=None):
+                      K_values, KP_extent, KP_influence, mode, *, epilogue=None, query_order=None):
     """Deformable second stage (:379-499)."""
     _check_enums(KP_influence, mode)
     q, s = query_points.contiguous(), support_points.contiguous()
@@ -126,7 +128,7 @@ def KPConv_deform_ops(query_points, support_points, neighbors_indices, features,
     ws = _lib.workspace(L.d3f_kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout), q.device)
     out = torch.empty((Nq, Cout), dtype=torch.float32, device=q.device)
     _lib.check(L.d3f_kpconv_deform_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp),
-                                           _lib.ptr(off), _lib.ptr(mod), _lib.ptr(W), _lib.ptr(packed_weight(W)), Nq, Ns, H, K, Cin, Cout,
+                                           _lib.ptr(off), _lib.ptr(mod), _lib.ptr(W), _lib.ptr(packed_weight(W)), _lib.ptr(query_order), Nq, Ns, H, K, Cin, Cout,
                                            float(KP_extent), _INFLUENCE[KP_influence], _MODE[mode], _lib.ptr(scale),
                                            _lib.ptr(shift), None, alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
                                            _lib.stream()), "d3f_kpconv_deform_forward")
@@ -145,18 +147,18 @@ def _kernel_points(K_radius, num_kpoints, device, fixed):
 
 
 def KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed="center", KP_extent=1.0,
-           KP_influence="linear", aggregation_mode="sum", *, epilogue=None):
+           KP_influence="linear", aggregation_mode="sum", *, epilogue=None, query_order=None):
     """:102-158 -- kernel-point disposition of radius 1.5*KP_extent, then KPConv_ops."""
     K_radius = 1.5 * KP_extent
     num_kpoints = int(K_values.shape[0])
     K_points = _kernel_points(K_radius, num_kpoints, query_points.device, fixed)
     return KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
-                      KP_influence, aggregation_mode, epilogue=epilogue)
+                      KP_influence, aggregation_mode, epilogue=epilogue, query_order=query_order)
 
 
 def KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values, fixed="center",
                       KP_extent=1.0, KP_influence="linear", aggregation_mode="sum", modulated=False, *,
-                      epilogue=None):
+                      epilogue=None, query_order=None):
     """:258-376 -- rigid KPConv producing 3K (4K if modulated) offsets (+ bias), then the deformed conv."""
     K_radius = 1.5 * KP_extent
     num_kpoints = int(K_values.shape[0])
@@ -171,7 +173,7 @@ def KPConv_deformable(query_points, support_points, neighbors_indices, features,
         K_values0 = torch.zeros((num_kpoints, K_values.shape[1], offset_dim), device=query_points.device)
         b0 = torch.zeros((offset_dim,), device=query_points.device)
     features0 = KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values0, KP_extent,
-                           KP_influence, aggregation_mode, bias=b0)
+                           KP_influence, aggregation_mode, bias=b0, query_order=query_order)
     if modulated:
         offsets = features0[:, :points_dim * num_kpoints].reshape(-1, num_kpoints, points_dim)
         modulations = 2 * torch.sigmoid(features0[:, points_dim * num_kpoints:])
@@ -180,4 +182,5 @@ def KPConv_deformable(query_points, support_points, neighbors_indices, features,
         modulations = None
     offsets = offsets * KP_extent
     return KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets,
-                             modulations, K_values, KP_extent, KP_influence, aggregation_mode, epilogue=epilogue)
+                             modulations, K_values, KP_extent, KP_influence, aggregation_mode, epilogue=epilogue,
+                             query_order=query_order)

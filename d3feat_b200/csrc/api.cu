@@ -89,6 +89,13 @@ int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int 
                                (cudaStream_t)stream);
 }
 
+int d3f_radius_neighbors_order(const void* workspace, int Ns, int B, float radius, const float* host_bbox,
+                               int* out_order, d3f_stream_t stream) {
+  D3F_REQUIRE(workspace != nullptr && (out_order != nullptr || Ns == 0), D3F_ERR_INVALID,
+              "d3f_radius_neighbors_order: null pointer");
+  return radius_neighbors_order(workspace, Ns, B, radius, host_bbox, out_order, (cudaStream_t)stream);
+}
+
 size_t d3f_kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
   return kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout);
 }
@@ -100,24 +107,24 @@ int d3f_pack_weight(const float* W, int K, int N, float* packed, d3f_stream_t st
 }
 
 int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const float* feat, const float* Kp,
-                       const float* W, const float* W_packed, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent, int influence,
+                       const float* W, const float* W_packed, const int* query_order, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent, int influence,
                        int mode, int normalize, const float* bn_scale, const float* bn_shift, const float* bias,
                        float leaky_alpha, float* out, void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
   D3F_REQUIRE(Nq == 0 || (q && s && idx && feat && Kp && W && out && workspace), D3F_ERR_INVALID,
               "d3f_kpconv_forward: null pointer");
-  return kpconv_forward_impl(false, q, s, idx, feat, Kp, nullptr, nullptr, W, W_packed, Nq, Ns, H, K, Cin, Cout, extent,
+  return kpconv_forward_impl(false, q, s, idx, feat, Kp, nullptr, nullptr, W, W_packed, query_order, Nq, Ns, H, K, Cin, Cout, extent,
                              influence, mode, normalize, bn_scale, bn_shift, bias, leaky_alpha, out, workspace,
                              workspace_bytes, (cudaStream_t)stream);
 }
 
 int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, const float* feat, const float* Kp,
                               const float* offsets, const float* modulations, const float* W, const float* W_packed,
-                              int Nq, int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, const float* bn_scale,
+                              const int* query_order, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, const float* bn_scale,
                               const float* bn_shift, const float* bias, float leaky_alpha, float* out,
                               void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
   D3F_REQUIRE(Nq == 0 || (q && s && idx && feat && Kp && W && out && workspace && offsets), D3F_ERR_INVALID,
               "d3f_kpconv_deform_forward: null pointer");
-  return kpconv_forward_impl(true, q, s, idx, feat, Kp, offsets, modulations, W, W_packed, Nq, Ns, H, K, Cin, Cout, extent,
+  return kpconv_forward_impl(true, q, s, idx, feat, Kp, offsets, modulations, W, W_packed, query_order, Nq, Ns, H, K, Cin, Cout, extent,
                              influence, mode, 0, bn_scale, bn_shift, bias, leaky_alpha, out, workspace,
                              workspace_bytes, (cudaStream_t)stream);
 }
@@ -138,6 +145,7 @@ int d3f_unary_forward(const float* x, const float* W, const float* W_packed, int
   ep.bias = bias;
   ep.residual = residual;
   ep.leaky_alpha = leaky_alpha;
+  ep.row_map = nullptr;
   if (W_packed != nullptr && tc_gemm_supported(x, Cin))
     return tc_gemm(x, W_packed, out, N, Cout, Cin, ep, (cudaStream_t)stream);
   return gemm_f32(x, W, out, N, Cout, Cin, ep, (cudaStream_t)stream);

@@ -133,6 +133,7 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
     int gm = m0 + ty * TM + i;
     if (gm >= M) continue;
     float rs = ep.rowscale ? ep.rowscale[gm] : 1.f;
+    const size_t orow = ep.row_map ? (size_t)ep.row_map[gm] : (size_t)gm;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int gn = n0 + tx * TN + j;
@@ -140,9 +141,9 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
       float y = acc[i][j] * rs;
       if (ep.bn_scale) y = fmaf(y, ep.bn_scale[gn], ep.bn_shift[gn]);
       if (ep.bias) y += ep.bias[gn];
-      if (ep.residual) y += ep.residual[(size_t)gm * N + gn];
+      if (ep.residual) y += ep.residual[orow * N + gn];
       if (ep.leaky_alpha >= 0.f) y = y > 0.f ? y : y * ep.leaky_alpha;
-      C[(size_t)gm * N + gn] = y;
+      C[orow * N + gn] = y;
     }
   }
 }

@@ -18,15 +18,17 @@ constexpr int kKMax = 16;        // kernel points are padded to 16 in shared mem
 
 struct Stage1Params {
   const float* q;
-  const float* s;
+  const float4* s4;           // [Ns+1] supports as (x, y, z, flag): flag = 1 if the feature-row sum > 0
+                              // (normalisation, :249-253); entry Ns is the shadow point (flag 0)
   const int* idx;
   const float* feat;
-  const unsigned char* flag;  // per support: feature-row sum > 0 (normalisation, :249-253); null if unused
+  int count_nn;               // accumulate the normalisation count
   const float* Kp;            // [K,3]
   const float* offsets;       // [Nq,K,3] or null (deformable)
   const float* modulations;   // [Nq,K] or null
   int Nq, Ns, H, Cin;
-  int n0, n1;                 // query chunk [n0, n1)
+  int n0, n1;                 // query chunk [n0, n1) (slots; slot i is query order[i] when order != null)
+  const int* order;           // optional visiting order of the queries (hash-grid cell order)
   float extent;               // KP_extent of this layer
   float inv_scale;            // 1/(2 extent) rigid (:215), 1/extent deformable (:461)
   float gauss_inv;            // 1/(2 sigma^2 + 1e-9), sigma = 0.3 extent (:218-222)
@@ -36,15 +38,29 @@ struct Stage1Params {
   float* inv_nn;              // [n1-n0] or null
 };
 
-__global__ void __launch_bounds__(256) rowsum_flag_kernel(const float* __restrict__ feat, int Ns, int Cin,
-                                                          unsigned char* __restrict__ flag) {
+// One warp per support point: pack (x, y, z, flag) so that phase A needs ONE 16-byte load per neighbour instead of
+// three scattered 4-byte loads plus a flag byte; entry Ns is the shadow point. mode 0: flag = 0, 1: flag = (row sum
+// of the features > 0) (:250-251), 2: flag slot carries the scalar feature itself (Cin = 1 kernel).
+__global__ void __launch_bounds__(256) prep_supports_kernel(const float* __restrict__ s, const float* __restrict__ feat,
+                                                            int Ns, int Cin, int mode, float shadow,
+                                                            float4* __restrict__ s4) {
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= Ns) return;
-  float s = 0.f;
-  for (int c = lane; c < Cin; c += 32) s += feat[(size_t)warp * Cin + c];
+  if (warp > Ns) return;
+  if (warp == Ns) {
+    if (lane == 0) s4[Ns] = make_float4(shadow, shadow, shadow, 0.f);
+    return;
+  }
+  float w = 0.f;
+  if (mode == 1) {
+    float sum = 0.f;
+    for (int c = lane; c < Cin; c += 32) sum += feat[(size_t)warp * Cin + c];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) flag[warp] = s > 0.f ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    w = sum > 0.f ? 1.f : 0.f;
+  } else if (mode == 2) {
+    w = feat[warp];
+  }
+  if (lane == 0) s4[warp] = make_float4(s[3 * (size_t)warp], s[3 * (size_t)warp + 1], s[3 * (size_t)warp + 2], w);
 }
 
 template <int K, int VEC, bool DEFORM>
@@ -55,16 +71,17 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Para
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = p.n0 + blockIdx.x * kS1Warps + warp;
   if (n >= p.n1) return;  // warp-uniform
+  const int qid = p.order ? p.order[n] : n;
 
   // kernel points of this query (rigid: shared by all queries; deformable: Kp + offsets[n])
   for (int t = lane; t < K * 3; t += 32) {
     float v = p.Kp[t];
-    if (DEFORM) v += p.offsets[(size_t)n * K * 3 + t];
+    if (DEFORM) v += p.offsets[(size_t)qid * K * 3 + t];
     kp_s[warp][t] = v;
   }
   for (int t = K * 3 + lane; t < kKMax * 3; t += 32) kp_s[warp][t] = 0.f;
-  const float qx = p.q[3 * (size_t)n], qy = p.q[3 * (size_t)n + 1], qz = p.q[3 * (size_t)n + 2];
-  const int* row = p.idx + (size_t)n * p.H;
+  const float qx = p.q[3 * (size_t)qid], qy = p.q[3 * (size_t)qid + 1], qz = p.q[3 * (size_t)qid + 2];
+  const int* row = p.idx + (size_t)qid * p.H;
   const float ext2 = p.extent * p.extent;
   __syncwarp();
 
@@ -85,12 +102,8 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Para
       int id = (h < p.H) ? row[h] : p.Ns;
       if (id < 0 || id > p.Ns) id = p.Ns;  // -1 padding of the non-batch op behaves like the shadow
       const bool real = id < p.Ns;
-      float rx, ry, rz;
-      if (real) {
-        rx = p.s[3 * (size_t)id] - qx; ry = p.s[3 * (size_t)id + 1] - qy; rz = p.s[3 * (size_t)id + 2] - qz;
-      } else {
-        rx = p.shadow - qx; ry = p.shadow - qy; rz = p.shadow - qz;
-      }
+      const float4 sp = __ldg(&p.s4[id]);   // entry Ns = shadow point
+      const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
       float w[kKMax];
       float dmin = 3.0e38f;
       int kmin = 0;
@@ -114,10 +127,7 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Para
       const bool keep = real && (!DEFORM || in_range);
 #pragma unroll
       for (int k = 0; k < kKMax; ++k) wts[warp][lane * kWStride + k] = (keep && k < K) ? w[k] : 0.f;
-      if (c0 == 0 && p.flag != nullptr) {
-        bool cnt = real && p.flag[id] != 0;
-        nn_count += __popc(__ballot_sync(0xffffffffu, cnt));
-      }
+      if (c0 == 0 && p.count_nn) nn_count += __popc(__ballot_sync(0xffffffffu, sp.w > 0.f));
       const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
       __syncwarp();
 
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Para
       float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)n * K + k] : 1.f;
+        float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)qid * K + k] : 1.f;
         if (VEC == 4) {
           *reinterpret_cast<float4*>(dst + (size_t)k * p.Cin) =
               make_float4(acc[k][0] * mod, acc[k][1 % VEC] * mod, acc[k][2 % VEC] * mod, acc[k][3 % VEC] * mod);
@@ -216,7 +226,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 template <int CPL, int QPW, bool DEFORM>
-__global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1_v2_kernel(Stage1Params p) {
+#ifndef D3F_S1_MINB
+#define D3F_S1_MINB 5
+#endif
+#ifndef D3F_S1_UNROLL
+#define D3F_S1_UNROLL 4
+#endif
+__global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpconv_stage1_v2_kernel(Stage1Params p) {
   constexpr int K = 15, KP = 16;
   constexpr int LPQ = 32 / QPW;  // lanes (= neighbour slots per pass) per query
   static_assert(CPL == 2 || CPL == 4, "channels per lane");
@@ -228,7 +244,8 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
   if (nfirst >= p.n1) return;  // warp-uniform
   const int n = nfirst + sub;
   const bool qvalid = n < p.n1;
-  const int nq = qvalid ? n : nfirst;  // invalid half-warps shadow the first query (results discarded)
+  const int nslot = qvalid ? n : nfirst;  // invalid half-warps shadow the first query (results discarded)
+  const int nq = p.order ? p.order[nslot] : nslot;
 
   for (int t = sl; t < KP * 3; t += LPQ) {
     float v = t < K * 3 ? p.Kp[t] : 0.f;
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
   const int* row = p.idx + (size_t)nq * p.H;
   const float ext2 = p.extent * p.extent;
   const unsigned gshift = (unsigned)(sub * LPQ);
-  const unsigned gmask = LPQ == 32 ? 0xffffffffu : 0xffffu;
+  const unsigned gmask = LPQ == 32 ? 0xffffffffu : ((1u << LPQ) - 1u);
   float* wq = &wts[warp][sub * LPQ * kWStride];
   __syncwarp();
 
@@ -259,12 +276,8 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
       int id = (h < p.H) ? row[h] : p.Ns;
       if (id < 0 || id > p.Ns) id = p.Ns;
       const bool real = id < p.Ns;
-      float rx, ry, rz;
-      if (real) {
-        rx = p.s[3 * (size_t)id] - qx; ry = p.s[3 * (size_t)id + 1] - qy; rz = p.s[3 * (size_t)id + 2] - qz;
-      } else {
-        rx = p.shadow - qx; ry = p.shadow - qy; rz = p.shadow - qz;
-      }
+      const float4 sp = __ldg(&p.s4[id]);   // entry Ns = shadow point
+      const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
       float w[KP];
       float dmin = 3.0e38f;
       int kmin = 0;
@@ -282,6 +295,10 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
         w[k] = wk;
       }
       w[K] = 0.f;
+#ifdef D3F_S1_SKIP_A
+#pragma unroll
+      for (int k = 0; k < K; ++k) w[k] = rx * 1e-9f + 0.5f;
+#endif
       if (p.closest) {
 #pragma unroll
         for (int k = 0; k < K; ++k) w[k] = (k == kmin) ? w[k] : 0.f;
@@ -291,18 +308,19 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
       for (int kq = 0; kq < KP / 4; ++kq)
         *reinterpret_cast<float4*>(&wq[sl * kWStride + 4 * kq]) =
             keep ? make_float4(w[4 * kq], w[4 * kq + 1], w[4 * kq + 2], w[4 * kq + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 == 0 && p.flag != nullptr) {
-        bool cnt = real && p.flag[id] != 0;
-        nn_count += __popc((__ballot_sync(0xffffffffu, cnt) >> gshift) & gmask);
-      }
+      if (c0 == 0 && p.count_nn) nn_count += __popc((__ballot_sync(0xffffffffu, sp.w > 0.f) >> gshift) & gmask);
       unsigned m = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
       int cnt = __popc(m);
-      if (QPW == 2) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
+      if (QPW >= 2) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
+      if (QPW >= 4) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 8));
       __syncwarp();
 
       // ---- phase B: both half-warps walk their kept neighbours in lockstep, kUnroll per step: all row loads
       //      of a step are issued before the first FMA consumes one (memory-level parallelism) -------------
-      constexpr int kUnroll = CPL == 4 ? 2 : 4;
+      constexpr int kUnroll = CPL == 4 ? 2 : D3F_S1_UNROLL;
+#ifdef D3F_S1_SKIP_B
+      cnt = 0;
+#endif
       for (int it = 0; it < cnt; it += kUnroll) {
         int hh[kUnroll];
         float f[kUnroll][CPL];
@@ -344,11 +362,15 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
     }
 
     // ---- write wf[n, k, c .. c+CPL) (optionally modulated, :489-490) ------------------------------------
+#ifdef D3F_S1_SKIP_STORE
+    if (qvalid && acc[0][0].x == 123.456f) {
+#else
     if (qvalid) {
+#endif
       float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)n * K + k] : 1.f;
+        const float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)nq * K + k] : 1.f;
         float o[CPL];
 #pragma unroll
         for (int v = 0; v < CPL; ++v) o[v] = ((k & 1) ? acc[k / 2][v].y : acc[k / 2][v].x) * mod;
@@ -360,12 +382,205 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 3 : 5) kpconv_stage1
   if (p.inv_nn != nullptr && qvalid && sl == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Stage 1, staged version: the gather is the latency problem (ncu: long-scoreboard stalls at every row load,
+// profiles/r1_notes.md), so a warp first issues ALL row gathers of its query group as asynchronous 16-byte copies
+// into shared memory (cp.async, zero-fill for shadow / dropped neighbours), evaluates the kernel-point correlation
+// weights while they are in flight, and then runs the FFMA2 loop entirely out of shared memory.
+//   per warp: feature tile kHT x 512 B (kHT neighbour slots x QPW queries x LPQ lanes x 16 B) + weight tile.
+constexpr int kHT = 40;                                   // neighbour slots staged per pass over H
+constexpr int kS3FeatFloats = kHT * 128;                  // 512 B per slot row
+constexpr int kS3WarpFloats = kS3FeatFloats + 32 * kWStride + 4 * kKMax * 3;
+constexpr int kS3SmemBytes = kS1Warps * kS3WarpFloats * 4;
+
+__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, bool valid) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+
+template <int CPL, int QPW, bool DEFORM>
+__global__ void __launch_bounds__(kS1Warps * 32, 2) kpconv_stage1_v3_kernel(Stage1Params p) {
+  constexpr int K = 15, KP = 16;
+  constexpr int LPQ = 32 / QPW;
+  constexpr int NJ = (kHT + LPQ - 1) / LPQ;   // slot groups per staged pass
+  static_assert(CPL == 4, "one 16-byte copy per lane and slot");
+  extern __shared__ __align__(16) float s3_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* ftile = s3_smem + warp * kS3WarpFloats;
+  float* wts = ftile + kS3FeatFloats;
+  float* kp_s = wts + 32 * kWStride;           // [QPW][KP*3]
+  const int sub = lane / LPQ, sl = lane % LPQ;
+  const int nfirst = p.n0 + (blockIdx.x * kS1Warps + warp) * QPW;
+  if (nfirst >= p.n1) return;  // warp-uniform
+  const int n = nfirst + sub;
+  const bool qvalid = n < p.n1;
+  const int nslot = qvalid ? n : nfirst;
+  const int nq = p.order ? p.order[nslot] : nslot;
+
+  for (int t = sl; t < KP * 3; t += LPQ) {
+    float v = t < K * 3 ? p.Kp[t] : 0.f;
+    if (DEFORM && t < K * 3) v += p.offsets[(size_t)nq * K * 3 + t];
+    kp_s[sub * KP * 3 + t] = v;
+  }
+  const float qx = p.q[3 * (size_t)nq], qy = p.q[3 * (size_t)nq + 1], qz = p.q[3 * (size_t)nq + 2];
+  const int* row = p.idx + (size_t)nq * p.H;
+  const float ext2 = p.extent * p.extent;
+  const unsigned gshift = (unsigned)(sub * LPQ);
+  const unsigned gmask = LPQ == 32 ? 0xffffffffu : ((1u << LPQ) - 1u);
+  float* wq = wts + sub * LPQ * kWStride;
+  const float* kq = kp_s + sub * KP * 3;
+  __syncwarp();
+
+  int nn_count = 0;
+  constexpr int c_step = LPQ * CPL;
+  for (int c0 = 0; c0 < p.Cin; c0 += c_step) {
+    float2 acc[KP / 2][CPL];
+#pragma unroll
+    for (int j = 0; j < KP / 2; ++j)
+#pragma unroll
+      for (int v = 0; v < CPL; ++v) acc[j][v] = make_float2(0.f, 0.f);
+    const int c = c0 + sl * CPL;
+
+    for (int ht0 = 0; ht0 < p.H; ht0 += kHT) {
+      // ---- phase 0: neighbour ids of this lane's slots, support points, and ALL row gathers in flight --------
+      int id[NJ];
+      float4 sp[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int hs = j * LPQ + sl;          // slot inside the staged pass
+        const int h = ht0 + hs;
+        int v = (hs < kHT && h < p.H) ? row[h] : p.Ns;
+        if (v < 0 || v > p.Ns) v = p.Ns;
+        id[j] = v;
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) sp[j] = __ldg(&p.s4[id[j]]);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+#pragma unroll
+        for (int t = 0; t < LPQ; ++t) {
+          const int hs = j * LPQ + t;
+          if (hs < kHT) {
+            const int idh = __shfl_sync(0xffffffffu, id[j], (int)gshift + t);
+            const bool ok = idh < p.Ns && qvalid;
+            cp_async16_zfill(ftile + hs * 128 + lane * 4, p.feat + (size_t)(ok ? idh : 0) * p.Cin + c, ok);
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        // ---- phase A: correlation weights of slot group j (overlaps the copies for j == 0) --------------------
+        const bool real = id[j] < p.Ns;
+        const float rx = sp[j].x - qx, ry = sp[j].y - qy, rz = sp[j].z - qz;
+        float w[KP];
+        float dmin = 3.0e38f;
+        int kmin = 0;
+        bool in_range = false;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          float dx = rx - kq[3 * k], dy = ry - kq[3 * k + 1], dz = rz - kq[3 * k + 2];
+          float d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < dmin) { dmin = d2; kmin = k; }
+          in_range = in_range || (d2 < ext2);
+          float wk;
+          if (p.influence == D3F_INFLUENCE_LINEAR) wk = fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
+          else if (p.influence == D3F_INFLUENCE_GAUSSIAN) wk = __expf(-d2 * p.gauss_inv);
+          else wk = DEFORM ? (d2 < ext2 ? 1.f : 0.f) : 1.f;
+          w[k] = wk;
+        }
+        w[K] = 0.f;
+        if (p.closest) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) w[k] = (k == kmin) ? w[k] : 0.f;
+        }
+        const bool keep = real && qvalid && (!DEFORM || in_range);
+#pragma unroll
+        for (int kk = 0; kk < KP / 4; ++kk)
+          *reinterpret_cast<float4*>(&wq[sl * kWStride + 4 * kk]) =
+              keep ? make_float4(w[4 * kk], w[4 * kk + 1], w[4 * kk + 2], w[4 * kk + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 == 0 && p.count_nn) nn_count += __popc((__ballot_sync(0xffffffffu, sp[j].w > 0.f) >> gshift) & gmask);
+        unsigned m = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
+        int cnt = __popc(m);
+        if (QPW >= 2) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
+        if (QPW >= 4) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 8));
+        if (j == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+
+        // ---- phase B: FFMA2 over the kept slots, features and weights both from shared memory ----------------
+        for (int it = 0; it < cnt; ++it) {
+          const bool act = m != 0;
+          const int t = act ? __ffs(m) - 1 : 0;
+          m &= m - 1;
+          float4 f = *reinterpret_cast<const float4*>(ftile + (j * LPQ + t) * 128 + lane * 4);
+          if (!act) f = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* wp = reinterpret_cast<const float4*>(&wq[t * kWStride]);
+          float2 wpair[KP / 2];
+#pragma unroll
+          for (int kk = 0; kk < KP / 4; ++kk) {
+            float4 tw = wp[kk];
+            wpair[2 * kk] = make_float2(tw.x, tw.y);
+            wpair[2 * kk + 1] = make_float2(tw.z, tw.w);
+          }
+          const float fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+          for (int v = 0; v < CPL; ++v) {
+            const float2 fd = make_float2(fv[v], fv[v]);
+#pragma unroll
+            for (int jj = 0; jj < KP / 2; ++jj) acc[jj][v] = ffma2(wpair[jj], fd, acc[jj][v]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    if (qvalid) {
+      float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)nq * K + k] : 1.f;
+        float o[CPL];
+#pragma unroll
+        for (int v = 0; v < CPL; ++v) o[v] = ((k & 1) ? acc[k / 2][v].y : acc[k / 2][v].x) * mod;
+        *reinterpret_cast<float4*>(dst + (size_t)k * p.Cin) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+  if (p.inv_nn != nullptr && qvalid && sl == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
+}
+
+template <int QPW, bool DEFORM>
+static int launch_stage1_v3(const Stage1Params& p, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    D3F_CUDA(cudaFuncSetAttribute(kpconv_stage1_v3_kernel<4, QPW, DEFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kS3SmemBytes));
+    configured = true;
+  }
+  int nq = p.n1 - p.n0;
+  kpconv_stage1_v3_kernel<4, QPW, DEFORM><<<ceil_div(nq, kS1Warps * QPW), kS1Warps * 32, kS3SmemBytes, stream>>>(p);
+  D3F_LAUNCH_CHECK("kpconv_stage1_v3_kernel");
+  return D3F_OK;
+}
+
 template <int K, bool DEFORM>
 static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
   int nq = p.n1 - p.n0;
   bool al16 = (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.wf) & 15) == 0;
+#ifdef D3F_STAGED   // measured slower than the direct-gather kernel on B200 (profiles/r1_notes.md); kept for experiments
+  if (K == 15 && al16 && p.Cin % 128 == 0) return launch_stage1_v3<1, DEFORM>(p, stream);
+  if (K == 15 && al16 && p.Cin == 64) return launch_stage1_v3<2, DEFORM>(p, stream);
+  if (K == 15 && al16 && p.Cin == 32) return launch_stage1_v3<4, DEFORM>(p, stream);
+#endif
+  // (channels per lane, queries per warp): every broadcast weight read should feed as much math as possible
   if (K == 15 && al16 && p.Cin % 128 == 0) {
     kpconv_stage1_v2_kernel<4, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
+  } else if (K == 15 && al16 && p.Cin == 64) {
+    kpconv_stage1_v2_kernel<4, 2, DEFORM><<<ceil_div(nq, kS1Warps * 2), kS1Warps * 32, 0, stream>>>(p);
+  } else if (K == 15 && al16 && p.Cin == 32) {
+    kpconv_stage1_v2_kernel<4, 4, DEFORM><<<ceil_div(nq, kS1Warps * 4), kS1Warps * 32, 0, stream>>>(p);
   } else if (K == 15 && al16 && p.Cin % 64 == 0) {
     kpconv_stage1_v2_kernel<2, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
   } else if (K == 15 && al16 && p.Cin % 32 == 0) {
@@ -384,13 +599,14 @@ static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
 // wf[k] = sum_h w[h,k] f[h], then lanes <-> output channels for out[c] = (sum_k wf[k] W[k,0,c]) / nn + epilogue.
 // One kernel, nothing but the output row is written.
 struct Cin1Params {
-  const float* q; const float* s; const int* idx; const float* feat; const float* Kp; const float* W;
+  const float* q; const float4* s4; const int* idx; const float* Kp; const float* W;
   int Nq, Ns, H, Cout;
   float inv_scale, gauss_inv;
   int influence, closest, normalize;
   float shadow;
   const float* bn_scale; const float* bn_shift; const float* bias;
   float leaky_alpha;
+  const int* order;
   float* out;
 };
 
@@ -400,8 +616,9 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
   for (int t = threadIdx.x; t < K * 3; t += blockDim.x) kp_s[t] = p.Kp[t];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (n >= p.Nq) return;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= p.Nq) return;
+  const int n = p.order ? p.order[slot] : slot;
   const float qx = p.q[3 * (size_t)n], qy = p.q[3 * (size_t)n + 1], qz = p.q[3 * (size_t)n + 2];
   const int* row = p.idx + (size_t)n * p.H;
   float wf[K];
@@ -412,13 +629,9 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
     const int h = h0 + lane;
     int id = (h < p.H) ? row[h] : p.Ns;
     if (id < 0 || id > p.Ns) id = p.Ns;
-    const bool real = id < p.Ns;
-    float f = 0.f, rx = p.shadow - qx, ry = p.shadow - qy, rz = p.shadow - qz;
-    if (real) {
-      f = p.feat[id];
-      rx = p.s[3 * (size_t)id] - qx; ry = p.s[3 * (size_t)id + 1] - qy; rz = p.s[3 * (size_t)id + 2] - qz;
-    }
-    nn += __popc(__ballot_sync(0xffffffffu, real && f > 0.f));
+    const float4 sp = __ldg(&p.s4[id]);   // (x, y, z, feature); entry Ns = shadow point with feature 0
+    const float f = sp.w, rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
+    nn += __popc(__ballot_sync(0xffffffffu, f > 0.f));
     float w[K];
     float dmin = 3.0e38f;
     int kmin = 0;
@@ -474,13 +687,14 @@ size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
   size_t b = 0;
   b += align_up((size_t)chunk * K * Cin * sizeof(float), 256);
   b += align_up((size_t)chunk * sizeof(float), 256);
-  b += align_up((size_t)(Ns + 1), 256);
+  b += align_up((size_t)(Ns + 1) * sizeof(float4), 256);
   return b + 1024;
 }
 
 int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* idx, const float* feat,
                         const float* Kp, const float* offsets, const float* modulations, const float* W,
-                        const float* W_packed, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent,
+                        const float* W_packed, const int* query_order, int Nq, int Ns, int H, int K, int Cin, int Cout,
+                        float extent,
                         int influence, int mode, int normalize,
                         const float* bn_scale, const float* bn_shift, const float* bias, float leaky_alpha,
                         float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -502,11 +716,17 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   Carver cv(workspace, workspace_bytes);
   float* wf = cv.take<float>((size_t)chunk * K * Cin);
   float* inv_nn = cv.take<float>(chunk);
-  unsigned char* flag = cv.take<unsigned char>(Ns + 1);
-
+  float4* s4 = cv.take<float4>((size_t)Ns + 1);
+  const bool norm = normalize != 0 && !deform;
+  {
+    int pmode = (Cin == 1 && !deform) ? 2 : (norm ? 1 : 0);
+    prep_supports_kernel<<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, pmode, deform ? 1000.f : 1e6f,
+                                                                            s4);
+    D3F_LAUNCH_CHECK("prep_supports_kernel");
+  }
   if (Cin == 1 && !deform) {
     Cin1Params c1;
-    c1.q = q; c1.s = s; c1.idx = idx; c1.feat = feat; c1.Kp = Kp; c1.W = W;
+    c1.q = q; c1.s4 = s4; c1.idx = idx; c1.Kp = Kp; c1.W = W;
     c1.Nq = Nq; c1.Ns = Ns; c1.H = H; c1.Cout = Cout;
     c1.inv_scale = 1.f / (2.f * extent);
     float sg = extent * 0.3f;
@@ -514,18 +734,14 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     c1.influence = influence; c1.closest = mode == D3F_MODE_CLOSEST; c1.normalize = normalize != 0;
     c1.shadow = 1e6f;
     c1.bn_scale = bn_scale; c1.bn_shift = bn_shift; c1.bias = bias; c1.leaky_alpha = leaky_alpha;
+    c1.order = query_order;
     c1.out = out;
     kpconv_cin1_kernel<<<ceil_div(Nq * 32, 256), 256, 0, stream>>>(c1);
     D3F_LAUNCH_CHECK("kpconv_cin1_kernel");
     return D3F_OK;
   }
-  const bool norm = normalize != 0 && !deform;
-  if (norm && Ns > 0) {
-    rowsum_flag_kernel<<<ceil_div(Ns * 32, 256), 256, 0, stream>>>(feat, Ns, Cin, flag);
-    D3F_LAUNCH_CHECK("rowsum_flag_kernel");
-  }
   Stage1Params p;
-  p.q = q; p.s = s; p.idx = idx; p.feat = feat; p.flag = norm ? flag : nullptr;
+  p.q = q; p.s4 = s4; p.idx = idx; p.feat = feat; p.count_nn = norm ? 1 : 0;
   p.Kp = Kp; p.offsets = offsets; p.modulations = modulations;
   p.Nq = Nq; p.Ns = Ns; p.H = H; p.Cin = Cin;
   p.extent = extent;
@@ -537,6 +753,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   p.shadow = deform ? 1000.f : 1e6f;
   p.wf = wf;
   p.inv_nn = norm ? inv_nn : nullptr;
+  p.order = query_order;
   for (int n0 = 0; n0 < Nq; n0 += chunk) {
     p.n0 = n0;
     p.n1 = min(Nq, n0 + chunk);
@@ -546,10 +763,13 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     ep.rowscale = norm ? inv_nn : nullptr;
     ep.bn_scale = bn_scale; ep.bn_shift = bn_shift; ep.bias = bias; ep.residual = nullptr;
     ep.leaky_alpha = leaky_alpha;
+    // chunk rows are query SLOTS; with a visiting order the epilogue scatters row m to query order[n0 + m]
+    ep.row_map = query_order ? query_order + n0 : nullptr;
+    float* cbase = query_order ? out : out + (size_t)n0 * Cout;
     if (W_packed != nullptr && tc_gemm_supported(wf, K * Cin))
-      rc = tc_gemm(wf, W_packed, out + (size_t)n0 * Cout, p.n1 - n0, Cout, K * Cin, ep, stream);
+      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, stream);
     else
-      rc = gemm_f32(wf, W, out + (size_t)n0 * Cout, p.n1 - n0, Cout, K * Cin, ep, stream);
+      rc = gemm_f32(wf, W, cbase, p.n1 - n0, Cout, K * Cin, ep, stream);
     if (rc) return rc;
   }
   return D3F_OK;

@@ -136,6 +136,25 @@ int radius_neighbors_build(const float* supports, const int* s_batch_len, int B,
   return D3F_OK;
 }
 
+// Support indices in cell order (the payload of the sorted keys): a spatially coherent visiting order that
+// gather kernels can use for their queries when queries == supports.
+int radius_neighbors_order(const void* workspace, int Ns, int B, float radius, const float* host_bbox, int* out_order,
+                           cudaStream_t stream) {
+  D3F_REQUIRE(B >= 1 && radius > 0.f && host_bbox != nullptr, D3F_ERR_INVALID, "radius_neighbors_order: bad arguments");
+  if (Ns <= 0) return D3F_OK;
+  NbGrid g = make_grid(host_bbox, radius);
+  long long total = g.ncells * B;
+  D3F_REQUIRE(total <= kMaxGridCells, D3F_ERR_CAPACITY, "radius_neighbors: grid too large");
+  Carver cv(const_cast<void*>(workspace), ~(size_t)0);
+  NbWs w;
+  carve_nb(cv, Ns, B, total, w);
+  int bits = 1;
+  while (bits < 62 && (1ll << bits) < total) ++bits;
+  int cur = sort_num_passes(bits) & 1;
+  D3F_CUDA(cudaMemcpyAsync(out_order, w.sort.vals[cur], sizeof(int) * (size_t)Ns, cudaMemcpyDeviceToDevice, stream));
+  return D3F_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 constexpr int kNbWarps = 8;      // warps (= queries in flight) per CTA
 constexpr int kNbListCap = 512;  // hits kept in shared memory per query before the generic path

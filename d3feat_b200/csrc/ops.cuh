@@ -12,6 +12,7 @@ struct Epilogue {
   const float* bias;      // [N] or null
   const float* residual;  // [M,N] or null
   float leaky_alpha;      // < 0: none
+  const int* row_map;     // [M] or null: GEMM row m is written to output row row_map[m]
 };
 int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
 
@@ -37,6 +38,8 @@ int radius_neighbors_build(const float* supports, const int* s_batch_len, int B,
 int radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                            const float* host_bbox, const void* workspace, int* counts, int* out_max,
                            cudaStream_t stream);
+int radius_neighbors_order(const void* workspace, int Ns, int B, float radius, const float* host_bbox, int* out_order,
+                           cudaStream_t stream);
 int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                           const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
                           cudaStream_t stream);
@@ -45,7 +48,7 @@ int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, 
 size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
 int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* idx, const float* feat,
                         const float* Kp, const float* offsets, const float* modulations, const float* W,
-                        const float* W_packed, int Nq,
+                        const float* W_packed, const int* query_order, int Nq,
                         int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, int normalize,
                         const float* bn_scale, const float* bn_shift, const float* bias, float leaky_alpha,
                         float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream);

@@ -18,7 +18,6 @@ namespace d3f {
 
 constexpr int kTcBM = 128;       // rows per CTA (UMMA M)
 constexpr int kTcBK = 32;        // fp32 per k-chunk = one 128 B swizzle row
-constexpr int kTcStages = 2;   // 2 x (40..64 KB): two CTAs per SM for BN <= 64 overlap each other's phases
 constexpr int kTcProducerThreads = 128;
 constexpr int kTcThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
 
@@ -143,11 +142,17 @@ struct TcAcc {
 
 template <int BN>
 struct TcSmem {
+  // BN = 128: 3 x 64 KB stages, one CTA per SM. BN <= 64: 2 x (40..48 KB): two CTAs per SM overlap each other.
+  static constexpr int kStages = BN >= 128 ? 3 : 2;
   static constexpr int kABytes = kTcBM * 128;  // one image (hi or lo) of the A tile
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
-  static constexpr int kTotal = kTcStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, BN >= 128 ? 1 : 2)
@@ -155,22 +160,23 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
                int Kpad, int Npad, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   using S = TcSmem<BN>;
+  constexpr int kStages = S::kStages;
   // 1024 B alignment: SWIZZLE_128B atoms are 8 rows x 128 B and the swizzle uses absolute address bits
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + kTcStages * S::kStageBytes);
+  uint64_t* bars = (uint64_t*)(smem + kStages * S::kStageBytes);
   // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then the TMEM base address
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kTcStages + 1);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * kStages + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
   const int nk = Kpad / kTcBK;
 
   if (tid == 0) {
-    for (int s = 0; s < kTcStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(smem_u32(&bars[s]), kTcProducerThreads);
-      mbar_init(smem_u32(&bars[kTcStages + s]), 1);
+      mbar_init(smem_u32(&bars[kStages + s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * kTcStages]), 1);
+    mbar_init(smem_u32(&bars[2 * kStages]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -186,55 +192,63 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
 
   if (warp < 4) {
     // ===================== producers: global -> registers -> (hi, lo) -> swizzled shared memory ==========
+    // Software pipelined one chunk ahead: while chunk kt is split and stored, the A loads of chunk kt+1 are
+    // already in flight in registers and its (pre-split) B rows are in flight as cp.async into the next stage.
     const int chunk = tid & 7;      // 16-byte chunk inside the 128-byte row
     const int rsub = tid >> 3;      // 0..15: row inside a 16-row slab
     const float* Bhi = Bp;
     const float* Blo = Bp + (size_t)Npad * Kpad;
-    for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % kTcStages;
-      const uint32_t ph = (uint32_t)(kt / kTcStages) & 1u;
-      mbar_wait(smem_u32(&bars[kTcStages + s]), ph ^ 1u);
+    float4 a_cur[kTcBM / 16];
+    auto issue_chunk = [&](int kt, float4 (&a)[kTcBM / 16]) {
+      const int s = kt % kStages;
+      const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
+      mbar_wait(smem_u32(&bars[kStages + s]), ph ^ 1u);      // stage free (its MMAs retired)
       uint8_t* st = smem + s * S::kStageBytes;
       const int k0 = kt * kTcBK + chunk * 4;
-      // ---- A tile: 128 rows, 8 slabs of 16 rows
-      float4 a[kTcBM / 16];
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {
+        int row = it * 16 + rsub;
+        uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        size_t goff = (size_t)(n0 + row) * Kpad + k0;
+        cp_async16(smem_u32(st + 2 * S::kABytes + off), Bhi + goff);
+        cp_async16(smem_u32(st + 2 * S::kABytes + S::kBBytes + off), Blo + goff);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
 #pragma unroll
       for (int it = 0; it < kTcBM / 16; ++it) {
         int row = it * 16 + rsub;
         int gm = m0 + row;
-        a[it] = (gm < M && k0 < K) ? *reinterpret_cast<const float4*>(A + (size_t)gm * K + k0)
+        a[it] = (gm < M && k0 < K) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * K + k0))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      // ---- B tiles (already split): BN rows
-      float4 bh[BN / 16], bl[BN / 16];
-#pragma unroll
-      for (int it = 0; it < BN / 16; ++it) {
-        int row = it * 16 + rsub;
-        size_t off = (size_t)(n0 + row) * Kpad + k0;
-        bh[it] = *reinterpret_cast<const float4*>(Bhi + off);
-        bl[it] = *reinterpret_cast<const float4*>(Blo + off);
-      }
+    };
+    issue_chunk(0, a_cur);
+    for (int kt = 0; kt < nk; ++kt) {
+      const int s = kt % kStages;
+      uint8_t* st = smem + s * S::kStageBytes;
+      float4 a_next[kTcBM / 16];
+      const bool more = kt + 1 < nk;
+      if (more) issue_chunk(kt + 1, a_next);
 #pragma unroll
       for (int it = 0; it < kTcBM / 16; ++it) {
         int row = it * 16 + rsub;
         uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         float4 hi, lo;
-        split_tf32(a[it].x, hi.x, lo.x);
-        split_tf32(a[it].y, hi.y, lo.y);
-        split_tf32(a[it].z, hi.z, lo.z);
-        split_tf32(a[it].w, hi.w, lo.w);
+        split_tf32(a_cur[it].x, hi.x, lo.x);
+        split_tf32(a_cur[it].y, hi.y, lo.y);
+        split_tf32(a_cur[it].z, hi.z, lo.z);
+        split_tf32(a_cur[it].w, hi.w, lo.w);
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + S::kABytes + off) = lo;
       }
-#pragma unroll
-      for (int it = 0; it < BN / 16; ++it) {
-        int row = it * 16 + rsub;
-        uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        *reinterpret_cast<float4*>(st + 2 * S::kABytes + off) = bh[it];
-        *reinterpret_cast<float4*>(st + 2 * S::kABytes + S::kBBytes + off) = bl[it];
-      }
+      if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's B rows of chunk kt landed
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&bars[s]));
+      if (more) {
+#pragma unroll
+        for (int it = 0; it < kTcBM / 16; ++it) a_cur[it] = a_next[it];
+      }
     }
 
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global ============
@@ -242,7 +256,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
     // warp transposes them through a padded 32x33 shared tile (the stage buffers are free: every MMA that
     // read them has retired when the accumulator barrier fires), then lane <-> column: the per-column BN /
     // bias parameters sit in registers and every residual load / store is one coalesced 128-byte row segment.
-    mbar_wait(smem_u32(&bars[2 * kTcStages]), 0);
+    mbar_wait(smem_u32(&bars[2 * kStages]), 0);
     tc_fence_after();
     const int row = warp * 32 + lane;      // TMEM lane == tile row; warp w may only touch lanes [32w, 32w+32)
     const int gm = m0 + row;
@@ -252,16 +266,21 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
     const int rows_here = min(32, M - (m0 + warp * 32));   // rows of this warp that exist (<= 0: none)
     const bool has_bn = ep.bn_scale != nullptr, has_bias = ep.bias != nullptr, has_res = ep.residual != nullptr;
     const bool has_leaky = ep.leaky_alpha >= 0.f;
+    // output row of tile row (warp*32 + lane): identity, or the caller's row map (KPConv walks its queries in
+    // the hash grid's cell order and scatters the rows back)
+    const int my_orow = (gm < M) ? (ep.row_map ? ep.row_map[gm] : gm) : 0;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int gn = n0 + c0 + lane;
       const bool col_ok = gn < N;
-      const size_t base = (size_t)(m0 + warp * 32) * N + gn;
       // residual rows of this column chunk: all 32 coalesced loads are in flight before anything waits on them
       float res[32];
       if (has_res) {
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) res[rr] = (col_ok && rr < rows_here) ? ep.residual[base + (size_t)rr * N] : 0.f;
+        for (int rr = 0; rr < 32; ++rr) {
+          const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+          res[rr] = (col_ok && rr < rows_here) ? ep.residual[(size_t)orow * N + gn] : 0.f;
+        }
       }
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
@@ -278,15 +297,14 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
       const float sc = (has_bn && col_ok) ? ep.bn_scale[gn] : 1.f;
       const float sh = (has_bn && col_ok) ? ep.bn_shift[gn] : 0.f;
       const float bi = (has_bias && col_ok) ? ep.bias[gn] : 0.f;
-      if (col_ok) {
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {
-          if (rr < rows_here) {
-            float y = fmaf(tile[rr * 33 + lane], sc, sh) + bi;
-            if (has_res) y += res[rr];
-            if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
-            C[base + (size_t)rr * N] = y;
-          }
+      for (int rr = 0; rr < 32; ++rr) {
+        const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+        if (col_ok && rr < rows_here) {
+          float y = fmaf(tile[rr * 33 + lane], sc, sh) + bi;
+          if (has_res) y += res[rr];
+          if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
+          C[(size_t)orow * N + gn] = y;
         }
       }
       __syncwarp();
@@ -296,8 +314,8 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
     // ===================== MMA issuer (warp 4, one elected lane) ========================================
     const uint32_t idesc = make_idesc_tf32(kTcBM, BN);
     for (int kt = 0; kt < nk; ++kt) {
-      const int s = kt % kTcStages;
-      const uint32_t ph = (uint32_t)(kt / kTcStages) & 1u;
+      const int s = kt % kStages;
+      const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
       mbar_wait(smem_u32(&bars[s]), ph);
       tc_fence_after();
       if (lane == 0) {
@@ -312,8 +330,8 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
           umma_tf32(d, a_lo + adv, b_hi + adv, idesc, 1u);
           umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
         }
-        umma_commit(smem_u32(&bars[kTcStages + s]));                 // stage free once these MMAs retire
-        if (kt == nk - 1) umma_commit(smem_u32(&bars[2 * kTcStages]));  // accumulator complete
+        umma_commit(smem_u32(&bars[kStages + s]));                 // stage free once these MMAs retire
+        if (kt == nk - 1) umma_commit(smem_u32(&bars[2 * kStages]));  // accumulator complete
       }
       __syncwarp();
     }

@@ -105,22 +105,31 @@ def leaky_relu(features, alpha=0.2):
     return _affine_leaky(features, None, None, None, alpha)
 
 
-def KPConv(query_points, support_points, neighbors_indices, features, K_values, radius, config, *, epilogue=None):
+def _order(inputs, layer_ind):
+    orders = inputs.get("orders") if isinstance(inputs, dict) else None
+    if not orders or layer_ind >= len(orders):
+        return None
+    o = orders[layer_ind]
+    return o if (o is not None and o.numel() > 0) else None
+
+
+def KPConv(query_points, support_points, neighbors_indices, features, K_values, radius, config, *, epilogue=None,
+           query_order=None):
     """:86-103."""
     extent = config.KP_extent * radius / config.density_parameter
     return conv_ops.KPConv(query_points, support_points, neighbors_indices, features, K_values,
                            fixed=config.fixed_kernel_points, KP_extent=extent, KP_influence=config.KP_influence,
-                           aggregation_mode=config.convolution_mode, epilogue=epilogue)
+                           aggregation_mode=config.convolution_mode, epilogue=epilogue, query_order=query_order)
 
 
 def KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values, radius, config, *,
-                      epilogue=None):
+                      epilogue=None, query_order=None):
     """:106-124."""
     extent = config.KP_extent * radius / config.density_parameter
     return conv_ops.KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values,
                                       fixed=config.fixed_kernel_points, KP_extent=extent,
                                       KP_influence=config.KP_influence, aggregation_mode=config.convolution_mode,
-                                      modulated=config.modulated, epilogue=epilogue)
+                                      modulated=config.modulated, epilogue=epilogue, query_order=query_order)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -150,7 +159,7 @@ def simple_block(layer_ind, inputs, features, radius, fdim, config, training):
     _no_training(training)
     w = weight_variable([config.num_kernel_points, int(features.shape[1]), fdim])
     return KPConv(inputs["points"][layer_ind], inputs["points"][layer_ind], inputs["neighbors"][layer_ind], features,
-                  w, radius, config, epilogue=_bn_epilogue(config, 0.2))
+                  w, radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind))
 
 
 def _resnetb(layer_ind, inputs, features, radius, fdim, config, training, strided, deformable):
@@ -166,7 +175,7 @@ def _resnetb(layer_ind, inputs, features, radius, fdim, config, training, stride
                      radius, config, epilogue=_bn_epilogue(config, 0.2))
         else:
             x = conv(inputs["points"][layer_ind], inputs["points"][layer_ind], inputs["neighbors"][layer_ind], x, w,
-                     radius, config, epilogue=_bn_epilogue(config, 0.2))
+                     radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind))
     with variable_scope("shortcut"):
         shortcut = ind_max_pool(features, inputs["pools"][layer_ind]) if strided else features
         if int(shortcut.shape[1]) != 2 * fdim:

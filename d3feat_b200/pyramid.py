@@ -7,6 +7,8 @@ supports and that radius (conv_l, pool_l, and up_{l-1}), i.e. 5 grid builds inst
 matrices are produced directly at the calibrated width (the reference computes the full width and slices),
 so the only device->host reads are the number of cells after each subsampling and one bbox up front.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -65,7 +67,7 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
     if bbox is None:
         bbox = ops.host_bbox(pts)
     levels = _level_radii(config)
-    out = dict(points=[], neighbors=[], pools=[], upsamples=[], lengths=[])
+    out = dict(points=[], neighbors=[], pools=[], upsamples=[], lengths=[], orders=[])
     grids = {}
 
     def grid_for(level, supports, sb, radius):
@@ -80,9 +82,17 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
         p, b = level_pts[li], level_len[li]
         lim = int(neighborhood_limits[li])
         if lv["conv_r"] is not None:
-            conv_i = grid_for(li, p, b, lv["conv_r"]).fill(p, b, lim, p.shape[0])
+            g = grid_for(li, p, b, lv["conv_r"])
+            conv_i = g.fill(p, b, lim, p.shape[0])
+            # level 0 arrives in the caller's (arbitrary) order: hand the gather kernels the grid's cell order as
+            # visiting order. Deeper levels are already emitted in cell order by the subsampling.
+            # (measured on B200: no gain -- the gathers are L2-latency bound, not L1-locality bound -- so the hint
+            # is off unless D3F_QUERY_ORDER=1; profiles/r1_notes.md)
+            use_order = li == 0 and os.environ.get("D3F_QUERY_ORDER", "0") == "1"
+            order = g.order() if use_order else torch.zeros((0,), dtype=torch.int32, device=dev)
         else:
             conv_i = torch.zeros((0, 1), dtype=torch.int32, device=dev)
+            order = torch.zeros((0,), dtype=torch.int32, device=dev)
         if lv["dl"] is not None:
             pool_p, pool_b = ops.batch_grid_subsampling(p, b, lv["dl"], bbox=bbox)
             pool_i = grid_for(li, p, b, lv["pool_r"]).fill(pool_p, pool_b, lim, p.shape[0])
@@ -97,6 +107,7 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
         out["pools"].append(pool_i)
         out["upsamples"].append(up_i)
         out["lengths"].append(b)
+        out["orders"].append(order)
     return out
 
 

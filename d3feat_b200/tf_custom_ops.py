@@ -64,6 +64,13 @@ class NeighborGrid:
                                                 self._bbp, _lib.ptr(self.ws), self.ws.numel(), _lib.stream()),
                    "d3f_radius_neighbors_build")
 
+    def order(self):
+        """int32[Ns]: support indices in cell order (spatially coherent visiting order)."""
+        out = torch.empty((max(self.Ns, 1),), dtype=torch.int32, device=self.s.device)
+        _lib.check(_lib.lib().d3f_radius_neighbors_order(_lib.ptr(self.ws), self.Ns, self.B, self.radius, self._bbp,
+                                                         _lib.ptr(out), _lib.stream()), "d3f_radius_neighbors_order")
+        return out[:self.Ns]
+
     def count(self, queries, q_batches):
         Nq = int(queries.shape[0])
         counts = torch.empty((max(Nq, 1),), dtype=torch.int32, device=queries.device)

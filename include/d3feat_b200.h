@@ -104,6 +104,11 @@ int d3f_radius_neighbors_count(const float* queries, const int* q_batch_len, int
                                const float* supports, const int* s_batch_len, int B, int Ns,
                                float radius, const float* host_bbox, const void* workspace,
                                int* counts, int* out_max, d3f_stream_t stream);
+/* out_order[Ns]: the support indices in hash-grid cell order (a spatially coherent visiting order). Passing it
+ * as `query_order` to d3f_kpconv_forward when queries == supports makes neighbouring queries share their
+ * gathered rows in L1/L2; results are unchanged (each query still writes its own output row). */
+int d3f_radius_neighbors_order(const void* workspace, int Ns, int B, float radius,
+                               const float* host_bbox, int* out_order, d3f_stream_t stream);
 int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq,
                               const float* supports, const int* s_batch_len, int B, int Ns,
                               float radius, const float* host_bbox, const void* workspace, int cols,
@@ -131,8 +136,8 @@ int d3f_pack_weight(const float* W, int K, int N, float* packed, d3f_stream_t st
  * ------------------------------------------------------------------------------------------- */
 size_t d3f_kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
 int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const float* feat,
-                       const float* Kp, const float* W, const float* W_packed, int Nq, int Ns, int H,
-                       int K, int Cin,
+                       const float* Kp, const float* W, const float* W_packed, const int* query_order,
+                       int Nq, int Ns, int H, int K, int Cin,
                        int Cout, float extent, int influence, int mode, int normalize,
                        const float* bn_scale, const float* bn_shift, const float* bias,
                        float leaky_alpha, float* out, void* workspace, size_t workspace_bytes,
@@ -143,8 +148,8 @@ int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const flo
  * point are dropped (:435-451); optional modulations[n,K]; no neighbour-count normalisation. */
 int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, const float* feat,
                               const float* Kp, const float* offsets, const float* modulations,
-                              const float* W, const float* W_packed, int Nq, int Ns, int H, int K,
-                              int Cin, int Cout,
+                              const float* W, const float* W_packed, const int* query_order, int Nq,
+                              int Ns, int H, int K, int Cin, int Cout,
                               float extent, int influence, int mode, const float* bn_scale,
                               const float* bn_shift, const float* bias, float leaky_alpha,
                               float* out, void* workspace, size_t workspace_bytes,

@@ -98,6 +98,23 @@ def test_normalisation_counts_positive_feature_rows(cuda):
     assert rel_err(out, ref) < RTOL
 
 
+@pytest.mark.parametrize("Cin,Cout", [(1, 64), (32, 32), (64, 64), (128, 128), (48, 40)])
+def test_query_order_is_only_a_scheduling_hint(cuda, Cin, Cout):
+    """Walking the queries in a permuted (hash-grid cell) order must not change any output row."""
+    from d3feat_b200 import convolution_ops as co, tf_custom_ops as ops
+    rng = np.random.default_rng(11 + Cin)
+    q, s, idx, f, Kp, W = make_case(rng, 2500, 2500, 40, Cin, Cout, extent=0.08)
+    args = [t(x, cuda) for x in (q, s, idx, f, Kp, W)]
+    base = co.KPConv_ops(*args, 0.08, "linear", "sum")
+    perm = t(rng.permutation(2500).astype(np.int32), cuda)
+    assert torch.equal(co.KPConv_ops(*args, 0.08, "linear", "sum", query_order=perm), base)
+    one = torch.tensor([2500], dtype=torch.int32, device=cuda)
+    grid = ops.NeighborGrid(args[1], one, 0.2)
+    order = grid.order()
+    assert sorted(order.cpu().tolist()) == list(range(2500))
+    assert torch.equal(co.KPConv_ops(*args, 0.08, "linear", "sum", query_order=order), base)
+
+
 @pytest.mark.parametrize("modulated", [False, True])
 def test_kpconv_deformable(cuda, modulated):
     from d3feat_b200 import convolution_ops as co
