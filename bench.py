@@ -182,7 +182,7 @@ def main():
     from d3feat_b200 import _lib
     from d3feat_b200 import convolution_ops as co
     from d3feat_b200.encoder import KPFCNN
-    from d3feat_b200.distributed import all_gather_descriptors
+    from d3feat_b200.distributed import all_gather_descriptors_padded
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -203,12 +203,13 @@ def main():
     enc = KPFCNN(cfg, params, LIMITS, device=dev)
     bbox = np.concatenate([P.min(0), P.max(0)]).astype(np.float32)
 
+    gather_cap = max(64, n_points // 64)     # rows reserved per rank for the coarsest-level descriptors
+
     def step_resident():
         out = enc(P_dev, L_dev, bbox=bbox, decoder=False)
         desc = out["F"][-1]
-        rows = [int(x) for x in out["inputs"]["lengths"][-1].tolist()] if world > 1 else None
-        if world > 1:
-            desc, _, _ = all_gather_descriptors(desc, rows)
+        if world > 1:      # the one exchange step: NCCL all-gather of the per-fragment descriptors (sync-free)
+            desc, _ = all_gather_descriptors_padded(desc, out["inputs"]["lengths"][-1], gather_cap)
         return desc
 
     def step_e2e():
@@ -218,8 +219,7 @@ def main():
         out = enc(p, l, decoder=False)          # bbox computed on the device (one small D2H read)
         desc = out["F"][-1]
         if world > 1:
-            rows = [int(x) for x in out["inputs"]["lengths"][-1].tolist()]
-            desc, _, _ = all_gather_descriptors(desc, rows)
+            desc, _ = all_gather_descriptors_padded(desc, out["inputs"]["lengths"][-1], gather_cap)
         return desc.cpu()
 
     flush_buf = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)     # > 126 MB L2
@@ -259,7 +259,7 @@ def main():
     total_points = n_points * world
     value = total_points / (ms / 1000.0)
     e2e_value = total_points / (ms_e2e / 1000.0)
-    d2h = int(enc(P_dev, L_dev, bbox=bbox, decoder=False)["F"][-1].numel() * 4 * (world if world > 1 else 1))
+    d2h = int(step_e2e().numel() * 4)      # bytes of the host tensor the e2e step returns (per rank)
 
     # ---- roofline of the dominant kernel: the largest KPConv (level 0, 32 -> 32 on all level-0 points) --
     roof = None
@@ -287,8 +287,12 @@ def main():
         abytes = kpconv_algorithmic_bytes(Nq, H, 15, 32, 32)
         peak, peak_src = peaks()
         ach = abytes / (kms * 1e-3) / 1e9
+        # DRAM bytes of the op from the committed ncu capture (profiles/r1_v2_ncu_kpconv_metrics.txt): the stage-1
+        # kernel moves 14.6 MB per 26112-query chunk launch (cold caches); the gathered rows are L2 hits
+        n_chunks = -(-int(Nq) // 26112)
+        traffic = int(14.63e6 * n_chunks) if (args.fragments, args.points) == (8, 30000) else None
         roof = dict(bound="hbm", kernel="kpconv level-0 32->32 (stage-1 gather + stage-2 contraction)", achieved=ach,
-                    peak=peak, unit="GB/s", frac=ach / peak, traffic=None, peak_source=peak_src,
+                    peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=abytes, ms_per_launch=kms, Nq=int(Nq), H=int(H))
 
     cpu = None

@@ -227,7 +227,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 
 template <int CPL, int QPW, bool DEFORM>
 #ifndef D3F_S1_MINB
-#define D3F_S1_MINB 5
+#define D3F_S1_MINB 6
 #endif
 #ifndef D3F_S1_UNROLL
 #define D3F_S1_UNROLL 4
@@ -577,10 +577,12 @@ static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
   // (channels per lane, queries per warp): every broadcast weight read should feed as much math as possible
   if (K == 15 && al16 && p.Cin % 128 == 0) {
     kpconv_stage1_v2_kernel<4, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
+#ifdef D3F_WIDE_LANES   // (4 ch/lane, 2-4 queries/warp): measured 5-8 % slower than the mappings below on B200
   } else if (K == 15 && al16 && p.Cin == 64) {
     kpconv_stage1_v2_kernel<4, 2, DEFORM><<<ceil_div(nq, kS1Warps * 2), kS1Warps * 32, 0, stream>>>(p);
   } else if (K == 15 && al16 && p.Cin == 32) {
     kpconv_stage1_v2_kernel<4, 4, DEFORM><<<ceil_div(nq, kS1Warps * 4), kS1Warps * 32, 0, stream>>>(p);
+#endif
   } else if (K == 15 && al16 && p.Cin % 64 == 0) {
     kpconv_stage1_v2_kernel<2, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
   } else if (K == 15 && al16 && p.Cin % 32 == 0) {

@@ -370,7 +370,12 @@ bool tc_gemm_supported(const float* A, int K) {
 int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return D3F_OK;
   D3F_REQUIRE(tc_gemm_supported(A, K), D3F_ERR_INVALID, "tc_gemm: needs K %% 4 == 0 and 16-byte aligned A");
-  switch (tc_block_n(N)) {
+  int bn = tc_block_n(N);
+  // skinny-K, huge-M GEMMs (the level-0/1 unary convolutions) are bound by per-CTA fixed costs and the C write:
+  // 64-wide column tiles let two CTAs share an SM and overlap each other's load / MMA / epilogue phases. The packed
+  // image is the same (Npad is a multiple of 128, hence of 64).
+  if (bn == 128 && K <= 256 && M >= 8192) bn = 64;
+  switch (bn) {
     case 128: return launch_tc<128>(A, Bp, C, M, N, K, ep, stream);
     case 64: return launch_tc<64>(A, Bp, C, M, N, K, ep, stream);
     default: return launch_tc<32>(A, Bp, C, M, N, K, ep, stream);

@@ -13,39 +13,79 @@ def shard_fragments(n_fragments, rank, world_size):
     return [f for f in range(n_fragments) if f % world_size == rank]
 
 
-def all_gather_descriptors(local_desc, local_rows_per_fragment, group=None):
-    """local_desc: float32[sum(rows), D] descriptors of this rank's fragments (stacked);
-    local_rows_per_fragment: list[int]. Returns (desc_all [R, D], rows_all list[int], owner list[int]) with
-    the fragments of rank 0 first, then rank 1, ... (each rank's own order preserved).
-
-    Two collectives: a tiny all-gather of the row counts, then one all-gather of the descriptors padded to
-    the largest per-rank row count.
-    """
+def _world(group):
     if not dist.is_available() or not dist.is_initialized():
-        return local_desc, list(local_rows_per_fragment), [0] * len(local_rows_per_fragment)
-    world = dist.get_world_size(group)
+        return 1
+    return dist.get_world_size(group)
+
+
+def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group=None):
+    """Sync-free gather used on the hot path.
+
+    local_desc: float32[R, D] stacked descriptors of this rank's fragments (R is the tensor's shape, host-known);
+    rows_per_fragment: int tensor [F] ON THE DEVICE (the last pyramid level's stack lengths) -- it is never read
+    on the host here; capacity: rows reserved per rank (>= R on every rank).
+    Returns (gathered [world, capacity, D], meta [world, 1 + F] int64 = [R, rows per fragment...]), both on the
+    device; no host synchronisation, two collectives (one of them a few bytes).
+    """
+    R, D = local_desc.shape
+    if R > capacity:
+        raise ValueError("all_gather_descriptors_padded: %d rows exceed the per-rank capacity %d" % (R, capacity))
     dev = local_desc.device
-    D = local_desc.shape[1]
-    n_local = len(local_rows_per_fragment)
-    meta = torch.tensor([local_desc.shape[0], n_local], dtype=torch.int64, device=dev)
-    metas = [torch.zeros_like(meta) for _ in range(world)]
-    dist.all_gather(metas, meta, group=group)
-    rows = [int(m[0]) for m in metas]
-    nfrag = [int(m[1]) for m in metas]
-    max_rows, max_frag = max(rows), max(nfrag)
-    frag_rows = torch.zeros((max(max_frag, 1),), dtype=torch.int64, device=dev)
-    if n_local:
-        frag_rows[:n_local] = torch.tensor(local_rows_per_fragment, dtype=torch.int64, device=dev)
-    frag_all = [torch.zeros_like(frag_rows) for _ in range(world)]
-    dist.all_gather(frag_all, frag_rows, group=group)
-    padded = torch.zeros((max(max_rows, 1), D), dtype=local_desc.dtype, device=dev)
-    padded[:local_desc.shape[0]] = local_desc
-    gathered = torch.empty((world, max(max_rows, 1), D), dtype=local_desc.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered.view(-1, D), padded, group=group) if dev.type == "cuda" else \
+    world = _world(group)
+    meta = torch.cat([torch.tensor([R], dtype=torch.int64, device=dev), rows_per_fragment.to(torch.int64)])
+    padded = torch.zeros((capacity, D), dtype=local_desc.dtype, device=dev)
+    padded[:R] = local_desc
+    if world == 1:
+        return padded.unsqueeze(0), meta.unsqueeze(0)
+    metas = torch.empty((world, meta.numel()), dtype=torch.int64, device=dev)
+    gathered = torch.empty((world, capacity, D), dtype=local_desc.dtype, device=dev)
+    if dev.type == "cuda":
+        dist.all_gather_into_tensor(metas.view(-1), meta, group=group)
+        dist.all_gather_into_tensor(gathered.view(-1, D), padded, group=group)
+    else:
+        dist.all_gather(list(metas.unbind(0)), meta, group=group)
         dist.all_gather(list(gathered.unbind(0)), padded, group=group)
+    return gathered, metas
+
+
+def unpack_gathered(gathered, metas):
+    """Host-side compaction of the padded gather: (desc_all [sum R, D], rows_all list[int], owner list[int]);
+    rank 0's fragments first, then rank 1's, ... (each rank's own order preserved). Synchronises."""
+    m = metas.cpu()
+    world = m.shape[0]
+    rows = [int(m[r, 0]) for r in range(world)]
     desc_all = torch.cat([gathered[r, :rows[r]] for r in range(world)], 0)
     rows_all, owner = [], []
     for r in range(world):
-        rows_all += [int(x) for x in frag_all[r][:nfrag[r]]]
-        owner += [r] * nfrag[r]
+        per = [int(x) for x in m[r, 1:] if int(x) > 0]   # zero entries pad ranks that own fewer fragments
+        rows_all += per
+        owner += [r] * len(per)
+    return desc_all, rows_all, owner
+
+
+def all_gather_descriptors(local_desc, local_rows_per_fragment, group=None):
+    """Convenience form with exact shapes (reads sizes on the host): returns
+    (desc_all [R_total, D], rows_all list[int], owner list[int])."""
+    if _world(group) == 1:
+        return local_desc, list(local_rows_per_fragment), [0] * len(local_rows_per_fragment)
+    dev = local_desc.device
+    world = _world(group)
+    n_local = len(local_rows_per_fragment)
+    sizes = torch.tensor([local_desc.shape[0], n_local], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    cap = max(int(s[0]) for s in all_sizes)
+    fmax = max(int(s[1]) for s in all_sizes)
+    rows_t = torch.zeros((max(fmax, 1),), dtype=torch.int64, device=dev)
+    if n_local:
+        rows_t[:n_local] = torch.tensor(list(local_rows_per_fragment), dtype=torch.int64, device=dev)
+    gathered, metas = all_gather_descriptors_padded(local_desc, rows_t, max(cap, 1), group)
+    desc_all, _, _ = unpack_gathered(gathered, metas)
+    m = metas.cpu()
+    rows_all, owner = [], []
+    for r in range(world):
+        nf = int(all_sizes[r][1])
+        rows_all += [int(x) for x in m[r, 1:1 + nf]]
+        owner += [r] * nf
     return desc_all, rows_all, owner
