@@ -27,6 +27,8 @@ SYMBOLS = [
     ("d3f_radius_neighbors_count", _I, [_P, _P, _I, _P, _P, _I, _I, _F, _P, _P, _P, _P, _P]),
     ("d3f_radius_neighbors_fill", _I, [_P, _P, _I, _P, _P, _I, _I, _F, _P, _P, _I, _I, _P, _P]),
     ("d3f_kpconv_workspace_bytes", _Z, [_I, _I, _I, _I, _I, _I]),
+    ("d3f_pyramid_workspace_bytes", _Z, [_I, _P, _P, _P]),
+    ("d3f_pyramid_build", _I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
     ("d3f_packed_weight_floats", _Z, [_I, _I]),
     ("d3f_pack_weight", _I, [_P, _I, _I, _P, _P]),
     ("d3f_radius_neighbors_order", _I, [_P, _I, _I, _F, _P, _P, _P]),

@@ -100,6 +100,22 @@ size_t d3f_kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cou
   return kpconv_workspace_bytes(Nq, Ns, H, K, Cin, Cout);
 }
 
+size_t d3f_pyramid_workspace_bytes(int B, const d3f_pyramid_spec* spec, const int* capacity, const float* host_bbox) {
+  return pyramid_workspace_bytes(B, spec, capacity, host_bbox);
+}
+
+int d3f_pyramid_build(const float* points, const int* lengths, int B, int N0, const d3f_pyramid_spec* spec,
+                      const float* host_bbox, float* const* out_points, int* const* out_lengths,
+                      int* const* out_neighbors, int* const* out_pools, int* const* out_upsamples, const int* capacity,
+                      int* out_level_sizes, void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
+  D3F_REQUIRE((points != nullptr || N0 == 0) && lengths != nullptr && out_points && out_lengths && out_neighbors &&
+                  out_pools && out_upsamples && workspace,
+              D3F_ERR_INVALID, "d3f_pyramid_build: null pointer");
+  D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "d3f_pyramid_build: B=%d", B);
+  return pyramid_build(points, lengths, B, N0, spec, host_bbox, out_points, out_lengths, out_neighbors, out_pools,
+                       out_upsamples, capacity, out_level_sizes, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 size_t d3f_packed_weight_floats(int K, int N) { return tc_packed_floats(K, N); }
 
 int d3f_pack_weight(const float* W, int K, int N, float* packed, d3f_stream_t stream) {

@@ -690,6 +690,7 @@ size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
   b += align_up((size_t)chunk * K * Cin * sizeof(float), 256);
   b += align_up((size_t)chunk * sizeof(float), 256);
   b += align_up((size_t)(Ns + 1) * sizeof(float4), 256);
+  b += align_up(tc_gemm_split_ws_floats(chunk, Cout, K * Cin) * sizeof(float), 256);
   return b + 1024;
 }
 
@@ -719,6 +720,8 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   float* wf = cv.take<float>((size_t)chunk * K * Cin);
   float* inv_nn = cv.take<float>(chunk);
   float4* s4 = cv.take<float4>((size_t)Ns + 1);
+  size_t split_floats = tc_gemm_split_ws_floats(chunk, Cout, K * Cin);
+  float* split_ws = split_floats ? cv.take<float>(split_floats) : nullptr;
   const bool norm = normalize != 0 && !deform;
   {
     int pmode = (Cin == 1 && !deform) ? 2 : (norm ? 1 : 0);
@@ -769,7 +772,8 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     ep.row_map = query_order ? query_order + n0 : nullptr;
     float* cbase = query_order ? out : out + (size_t)n0 * Cout;
     if (W_packed != nullptr && tc_gemm_supported(wf, K * Cin))
-      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, stream);
+      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, stream,
+                   (p.n1 - n0 == chunk) ? split_ws : nullptr);
     else
       rc = gemm_f32(wf, W, cbase, p.n1 - n0, Cout, K * Cin, ep, stream);
     if (rc) return rc;

@@ -20,7 +20,10 @@ int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, cons
 size_t tc_packed_floats(int K, int N);
 int tc_pack_weight(const float* W, int K, int N, float* packed, cudaStream_t stream);
 bool tc_gemm_supported(const float* A, int K);
-int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
+int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
+            float* split_ws = nullptr);
+int tc_gemm_splits(int M, int N, int K);
+size_t tc_gemm_split_ws_floats(int M, int N, int K);
 
 // ---- grid.cu ----------------------------------------------------------------------------------------
 int launch_batch_start(const int* len, int B, int* start, cudaStream_t stream);
@@ -43,6 +46,13 @@ int radius_neighbors_order(const void* workspace, int Ns, int B, float radius, c
 int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                           const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
                           cudaStream_t stream);
+
+// ---- pyramid.cu -------------------------------------------------------------------------------------
+size_t pyramid_workspace_bytes(int B, const d3f_pyramid_spec* spec, const int* capacity, const float* host_bbox);
+int pyramid_build(const float* points, const int* lengths, int B, int N0, const d3f_pyramid_spec* spec,
+                  const float* host_bbox, float* const* out_points, int* const* out_lengths,
+                  int* const* out_neighbors, int* const* out_pools, int* const* out_upsamples, const int* capacity,
+                  int* out_level_sizes, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // ---- kpconv.cu --------------------------------------------------------------------------------------
 size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);

@@ -157,7 +157,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
 template <int BN>
 __global__ void __launch_bounds__(kTcThreads, BN >= 128 ? 1 : 2)
 tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ C, int M, int N, int K,
-               int Kpad, int Npad, Epilogue ep) {
+               int Kpad, int Npad, int chunks_per_split, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   using S = TcSmem<BN>;
   constexpr int kStages = S::kStages;
@@ -169,7 +169,10 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
-  const int nk = Kpad / kTcBK;
+  // split-K: CTA z owns the k-chunks [kt0, kt0 + nk) and writes raw partial sums to its own [M,N] slab of C
+  const int kt0 = blockIdx.z * chunks_per_split;
+  const int nk = min(Kpad / kTcBK - kt0, chunks_per_split);
+  C += (size_t)blockIdx.z * M * N;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -204,7 +207,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
       const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
       mbar_wait(smem_u32(&bars[kStages + s]), ph ^ 1u);      // stage free (its MMAs retired)
       uint8_t* st = smem + s * S::kStageBytes;
-      const int k0 = kt * kTcBK + chunk * 4;
+      const int k0 = (kt0 + kt) * kTcBK + chunk * 4;
 #pragma unroll
       for (int it = 0; it < BN / 16; ++it) {
         int row = it * 16 + rsub;
@@ -346,9 +349,27 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
   }
 }
 
+// fixed-order reduction of the split-K partials + the block epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
+                                                            Epilogue ep, float* __restrict__ C) {
+  long long total = (long long)M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int m = (int)(i / N), n = (int)(i % N);
+    float y = 0.f;
+    for (int z = 0; z < splits; ++z) y += part[(size_t)z * total + i];
+    if (ep.rowscale) y *= ep.rowscale[m];
+    if (ep.bn_scale) y = fmaf(y, ep.bn_scale[n], ep.bn_shift[n]);
+    if (ep.bias) y += ep.bias[n];
+    const size_t orow = ep.row_map ? (size_t)ep.row_map[m] : (size_t)m;
+    if (ep.residual) y += ep.residual[orow * N + n];
+    if (ep.leaky_alpha >= 0.f) y = y > 0.f ? y : y * ep.leaky_alpha;
+    C[orow * N + n] = y;
+  }
+}
+
 template <int BN>
 static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int splits = 1, float* split_ws = nullptr) {
   using S = TcSmem<BN>;
   static bool configured = false;   // idempotent attribute set; benign if two host threads race
   if (!configured) {
@@ -356,9 +377,25 @@ static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, in
     configured = true;
   }
   int Kpad = tc_padded_k(K), Npad = tc_padded_n(N);
-  dim3 grid(Npad / BN, ceil_div(M, kTcBM));
-  tc_gemm_kernel<BN><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, C, M, N, K, Kpad, Npad, ep);
+  const int nk = Kpad / kTcBK;
+  if (splits <= 1) {
+    dim3 grid(Npad / BN, ceil_div(M, kTcBM), 1);
+    tc_gemm_kernel<BN><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, C, M, N, K, Kpad, Npad, nk, ep);
+    D3F_LAUNCH_CHECK("tc_gemm_kernel");
+    return D3F_OK;
+  }
+  const int cps = ceil_div(nk, splits);
+  splits = ceil_div(nk, cps);
+  Epilogue raw;
+  raw.rowscale = nullptr; raw.bn_scale = nullptr; raw.bn_shift = nullptr; raw.bias = nullptr; raw.residual = nullptr;
+  raw.leaky_alpha = -1.f; raw.row_map = nullptr;
+  dim3 grid(Npad / BN, ceil_div(M, kTcBM), splits);
+  tc_gemm_kernel<BN><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
   D3F_LAUNCH_CHECK("tc_gemm_kernel");
+  long long total = (long long)M * N;
+  int blocks = (int)min((total + 255) / 256, (long long)kNumSMs * 8);
+  splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(split_ws, splits, M, N, ep, C);
+  D3F_LAUNCH_CHECK("splitk_reduce_kernel");
   return D3F_OK;
 }
 
@@ -367,7 +404,24 @@ bool tc_gemm_supported(const float* A, int K) {
 }
 
 // A[M,K] fp32 row-major, Bp = packed weight (tc_pack_weight), C[M,N]
-int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream) {
+// split-K plan for GEMMs that cannot fill the GPU with output tiles: returns the number of K splits (1 = none)
+int tc_gemm_splits(int M, int N, int K) {
+  int bn = tc_block_n(N);
+  long long ctas = (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / bn);
+  int nk = tc_padded_k(K) / kTcBK;
+  if (ctas >= 96 || nk < 32) return 1;
+  int s = (int)((kNumSMs + ctas - 1) / ctas);
+  if (s > 8) s = 8;
+  if (s > nk / 8) s = nk / 8;
+  return s < 2 ? 1 : s;
+}
+size_t tc_gemm_split_ws_floats(int M, int N, int K) {
+  int s = tc_gemm_splits(M, N, K);
+  return s > 1 ? (size_t)s * M * N : 0;
+}
+
+int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
+            float* split_ws) {
   if (M <= 0 || N <= 0) return D3F_OK;
   D3F_REQUIRE(tc_gemm_supported(A, K), D3F_ERR_INVALID, "tc_gemm: needs K %% 4 == 0 and 16-byte aligned A");
   int bn = tc_block_n(N);
@@ -375,10 +429,11 @@ int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, cons
   // 64-wide column tiles let two CTAs share an SM and overlap each other's load / MMA / epilogue phases. The packed
   // image is the same (Npad is a multiple of 128, hence of 64).
   if (bn == 128 && K <= 256 && M >= 8192) bn = 64;
+  const int splits = split_ws != nullptr ? tc_gemm_splits(M, N, K) : 1;
   switch (bn) {
-    case 128: return launch_tc<128>(A, Bp, C, M, N, K, ep, stream);
-    case 64: return launch_tc<64>(A, Bp, C, M, N, K, ep, stream);
-    default: return launch_tc<32>(A, Bp, C, M, N, K, ep, stream);
+    case 128: return launch_tc<128>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
+    case 64: return launch_tc<64>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
+    default: return launch_tc<32>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
   }
 }
 

@@ -2,11 +2,13 @@
 with big_neighborhood_filter (:399-406) and calibrate_neighbors (:572-673), on the GPU.
 
 The reference runs this loop on the CPU inside tf.data (13 radius searches + 4 grid subsamplings per batch).
-Here every level builds ONE hash grid over its points and reuses it for the three searches that share those
-supports and that radius (conv_l, pool_l, and up_{l-1}), i.e. 5 grid builds instead of 13; the neighbour
-matrices are produced directly at the calibrated width (the reference computes the full width and slices),
-so the only device->host reads are the number of cells after each subsampling and one bbox up front.
+Here the whole loop is ONE call into the library (d3f_pyramid_build): every level builds one hash grid per
+(supports, radius) pair and reuses it for the searches that share it (conv_l, pool_l, up_{l-1}: 5 grid builds
+instead of 13), the neighbour matrices are produced directly at the calibrated width (the reference computes the
+full width and slices), and the only device->host reads are the number of cells after each subsampling plus one
+bbox up front.
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -15,9 +17,21 @@ import torch
 from . import _lib
 from . import tf_custom_ops as ops
 
+MAX_LEVELS = 8
+
+
+class PyramidSpec(C.Structure):
+    """ctypes image of d3f_pyramid_spec (include/d3feat_b200.h)."""
+    _fields_ = [("n_levels", C.c_int),
+                ("conv_radius", C.c_float * MAX_LEVELS),
+                ("sub_dl", C.c_float * MAX_LEVELS),
+                ("pool_radius", C.c_float * MAX_LEVELS),
+                ("up_radius", C.c_float * MAX_LEVELS),
+                ("limit", C.c_int * MAX_LEVELS)]
+
 
 def _level_radii(config):
-    """(conv radius, subsample dl, pool radius, upsample radius, has_pool) per level, exactly as the loop of
+    """(conv radius, subsample dl, pool radius, upsample radius) per level, exactly as the loop of
     tf_descriptor_input derives them (:1312-1396)."""
     r_normal = config.first_subsampling_dl * config.KP_extent * 2.5
     arch = list(config.architecture)
@@ -53,6 +67,28 @@ def _level_radii(config):
     return levels
 
 
+def make_spec(config, neighborhood_limits):
+    levels = _level_radii(config)
+    if len(levels) > MAX_LEVELS:
+        raise ValueError("pyramid: %d levels exceed D3F_MAX_LEVELS" % len(levels))
+    spec = PyramidSpec()
+    spec.n_levels = len(levels)
+    for l, lv in enumerate(levels):
+        spec.conv_radius[l] = float(lv["conv_r"]) if lv["conv_r"] is not None else -1.0
+        spec.sub_dl[l] = float(lv["dl"]) if lv["dl"] is not None else -1.0
+        spec.pool_radius[l] = float(lv.get("pool_r", -1.0)) if lv["dl"] is not None else -1.0
+        spec.up_radius[l] = float(lv.get("up_r", -1.0)) if lv["dl"] is not None else -1.0
+        spec.limit[l] = int(neighborhood_limits[l])
+    return spec, levels
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr() if t is not None else None
+    return arr
+
+
 def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limits, bbox=None):
     """Returns the dict the blocks consume: points[L], neighbors[L], pools[L], upsamples[L], lengths[L]
     (placeholders of the reference's shapes at the last level, :1374-1377).
@@ -66,48 +102,52 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
     lens = _lib.i32(stacked_lengths, dev)
     if bbox is None:
         bbox = ops.host_bbox(pts)
-    levels = _level_radii(config)
+    bb = np.ascontiguousarray(bbox, dtype=np.float32)
+    bbp = bb.ctypes.data_as(C.c_void_p)
+    spec, levels = make_spec(config, neighborhood_limits)
+    L = spec.n_levels
+    N0, B = int(pts.shape[0]), int(lens.shape[0])
+    # a subsampled level can never have more points than its parent: every level gets the level-0 capacity
+    cap = [max(N0, 1)] * L
+    cap_arr = (C.c_int * L)(*cap)
+    lib = _lib.lib()
+    i32, f32 = torch.int32, torch.float32
+    out_pts = [None] + [torch.empty((cap[l], 3), dtype=f32, device=dev) for l in range(1, L)]
+    out_len = [None] + [torch.empty((B,), dtype=i32, device=dev) for l in range(1, L)]
+    lim = [int(neighborhood_limits[l]) for l in range(L)]
+    out_nb = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["conv_r"] is not None else None
+              for l in range(L)]
+    out_pool = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
+                for l in range(L)]
+    out_up = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
+              for l in range(L)]
+    nbytes = lib.d3f_pyramid_workspace_bytes(B, C.byref(spec), cap_arr, bbp)
+    if nbytes == 0:
+        raise _lib.D3FError("pyramid: hash grid too large for bbox %s" % bb.tolist())
+    ws = _lib.workspace(nbytes, dev)
+    sizes = (C.c_int * L)()
+    _lib.check(lib.d3f_pyramid_build(_lib.ptr(pts), _lib.ptr(lens), B, N0, C.byref(spec), bbp, _ptr_array(out_pts),
+                                     _ptr_array(out_len), _ptr_array(out_nb), _ptr_array(out_pool),
+                                     _ptr_array(out_up), cap_arr, sizes, _lib.ptr(ws), ws.numel(), _lib.stream()),
+               "d3f_pyramid_build")
+    n = [int(sizes[l]) for l in range(L)]
+    empty_i = torch.zeros((0, 1), dtype=i32, device=dev)
     out = dict(points=[], neighbors=[], pools=[], upsamples=[], lengths=[], orders=[])
-    grids = {}
-
-    def grid_for(level, supports, sb, radius):
-        key = (level, float(np.float32(radius)))
-        if key not in grids:
-            grids[key] = ops.NeighborGrid(supports, sb, radius, bbox)
-        return grids[key]
-
-    level_pts = [pts]
-    level_len = [lens]
-    for li, lv in enumerate(levels):
-        p, b = level_pts[li], level_len[li]
-        lim = int(neighborhood_limits[li])
-        if lv["conv_r"] is not None:
-            g = grid_for(li, p, b, lv["conv_r"])
-            conv_i = g.fill(p, b, lim, p.shape[0])
-            # level 0 arrives in the caller's (arbitrary) order: hand the gather kernels the grid's cell order as
-            # visiting order. Deeper levels are already emitted in cell order by the subsampling.
-            # (measured on B200: no gain -- the gathers are L2-latency bound, not L1-locality bound -- so the hint
-            # is off unless D3F_QUERY_ORDER=1; profiles/r1_notes.md)
-            use_order = li == 0 and os.environ.get("D3F_QUERY_ORDER", "0") == "1"
-            order = g.order() if use_order else torch.zeros((0,), dtype=torch.int32, device=dev)
+    for l in range(L):
+        out["points"].append(pts if l == 0 else out_pts[l][:n[l]])
+        out["lengths"].append(lens if l == 0 else out_len[l])
+        out["neighbors"].append(out_nb[l][:n[l]] if out_nb[l] is not None else empty_i)
+        if levels[l]["dl"] is not None and l + 1 < L:
+            out["pools"].append(out_pool[l][:n[l + 1]])
+            out["upsamples"].append(out_up[l][:n[l]])
         else:
-            conv_i = torch.zeros((0, 1), dtype=torch.int32, device=dev)
-            order = torch.zeros((0,), dtype=torch.int32, device=dev)
-        if lv["dl"] is not None:
-            pool_p, pool_b = ops.batch_grid_subsampling(p, b, lv["dl"], bbox=bbox)
-            pool_i = grid_for(li, p, b, lv["pool_r"]).fill(pool_p, pool_b, lim, p.shape[0])
-            up_i = grid_for(li + 1, pool_p, pool_b, lv["up_r"]).fill(p, b, lim, pool_p.shape[0])
-            level_pts.append(pool_p)
-            level_len.append(pool_b)
-        else:
-            pool_i = torch.zeros((0, 1), dtype=torch.int32, device=dev)
-            up_i = torch.zeros((0, 1), dtype=torch.int32, device=dev)
-        out["points"].append(p)
-        out["neighbors"].append(conv_i)
-        out["pools"].append(pool_i)
-        out["upsamples"].append(up_i)
-        out["lengths"].append(b)
-        out["orders"].append(order)
+            out["pools"].append(empty_i)
+            out["upsamples"].append(empty_i)
+        out["orders"].append(torch.zeros((0,), dtype=i32, device=dev))
+    # D3F_QUERY_ORDER=1: hand the level-0 gather kernels the hash grid's cell order as query visiting order
+    # (measured on B200: no gain -- the gathers are L2-latency bound, not locality bound; profiles/r1_notes.md)
+    if os.environ.get("D3F_QUERY_ORDER", "0") == "1" and levels[0]["conv_r"] is not None:
+        out["orders"][0] = ops.NeighborGrid(pts, lens, levels[0]["conv_r"], bb).order()
     return out
 
 

@@ -115,6 +115,33 @@ int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int 
                               int pad_value, int* out_idx, d3f_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The whole input pyramid of the encoder in ONE call: the loop of Dataset.tf_descriptor_input
+ * (datasets/common.py:1325-1397) with the neighbourhood caps of big_neighborhood_filter (:399-406).
+ * Level l: neighbors[l] = search(points_l, points_l, conv_radius[l]) (skipped if conv_radius <= 0);
+ * if sub_dl[l] > 0: points_{l+1} = grid_subsample(points_l, sub_dl[l]); pools[l] = search(points_{l+1}, points_l,
+ * pool_radius[l]); upsamples[l] = search(points_l, points_{l+1}, up_radius[l]). Every index matrix has exactly
+ * limit[l] columns (nearest first, padded with the number of supports). Output buffers are caller-allocated with
+ * `capacity[l]` rows per level; out_level_sizes (HOST int[n_levels]) receives the actual row counts. The call
+ * synchronises the stream once per subsampled level (the next level's launch sizes depend on the cell count).
+ * ------------------------------------------------------------------------------------------- */
+#define D3F_MAX_LEVELS 8
+typedef struct {
+  int n_levels;
+  float conv_radius[D3F_MAX_LEVELS];
+  float sub_dl[D3F_MAX_LEVELS];
+  float pool_radius[D3F_MAX_LEVELS];
+  float up_radius[D3F_MAX_LEVELS];
+  int limit[D3F_MAX_LEVELS];
+} d3f_pyramid_spec;
+size_t d3f_pyramid_workspace_bytes(int B, const d3f_pyramid_spec* spec, const int* capacity,
+                                   const float* host_bbox);
+int d3f_pyramid_build(const float* points, const int* lengths, int B, int N0,
+                      const d3f_pyramid_spec* spec, const float* host_bbox, float* const* out_points,
+                      int* const* out_lengths, int* const* out_neighbors, int* const* out_pools,
+                      int* const* out_upsamples, const int* capacity, int* out_level_sizes,
+                      void* workspace, size_t workspace_bytes, d3f_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Static weights for the tensor-core path. A weight matrix W[K,N] (row-major; for KPConv the [K*Cin, Cout]
  * view of K_values[K,Cin,Cout]) is packed ONCE into the K-major TF32 hi/lo images the tcgen05 kernels
  * consume (3xTF32 split: fp32-level accuracy on the 5th-gen tensor cores). Every forward entry point takes
