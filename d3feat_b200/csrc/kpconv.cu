@@ -331,6 +331,10 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
           m &= m - 1;
           const int idh = __shfl_sync(0xffffffffu, id, (int)gshift + hh[u]);
           const float* fp = p.feat + (size_t)idh * p.Cin + c;
+#ifdef D3F_S1_NO_LOAD
+          for (int v = 0; v < CPL; ++v) f[u][v] = act ? qx + (float)(idh + v) : 0.f;
+          (void)fp;
+#else
           if (CPL == 4) {
             float4 t = act ? __ldg(reinterpret_cast<const float4*>(fp)) : make_float4(0.f, 0.f, 0.f, 0.f);
             f[u][0] = t.x; f[u][1] = t.y; f[u][2 % CPL] = t.z; f[u][3 % CPL] = t.w;
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
             float2 t = act ? __ldg(reinterpret_cast<const float2*>(fp)) : make_float2(0.f, 0.f);
             f[u][0] = t.x; f[u][1] = t.y;
           }
+#endif
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -350,12 +355,17 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
             wpair[2 * kq] = make_float2(t.x, t.y);
             wpair[2 * kq + 1] = make_float2(t.z, t.w);
           }
+#ifdef D3F_S1_NO_FMA
+#pragma unroll
+          for (int v = 0; v < CPL; ++v) acc[0][v].x += f[u][v] * wpair[v % (KP / 2)].x;
+#else
 #pragma unroll
           for (int v = 0; v < CPL; ++v) {
             const float2 fd = make_float2(f[u][v], f[u][v]);
 #pragma unroll
             for (int j = 0; j < KP / 2; ++j) acc[j][v] = ffma2(wpair[j], fd, acc[j][v]);
           }
+#endif
         }
       }
       __syncwarp();
@@ -565,10 +575,179 @@ static int launch_stage1_v3(const Stage1Params& p, cudaStream_t stream) {
   return D3F_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Stage 1 on the tensor pipe (warp-level mma.sync.m16n8k8 TF32, 3xTF32 split; measured 277 TFLOP/s on B200 =
+// 3.8x the FFMA2 fp32 peak, scripts/micro/mma_sync_rate.cu). Per query and 8-neighbour step:
+//     wf[16 kernel pts, channels] += W^T[16 x 8 neighbours] . F[8 neighbours x channels]
+// * A (correlation weights) is computed DIRECTLY in fragment layout: lane (g = lane/4, t = lane%4) evaluates the
+//   weights of neighbours {8s+t, 8s+t+4} against kernel points {g, g+8} -- they live in registers, no shared memory.
+// * B (gathered features) is loaded DIRECTLY in fragment layout. Column j of n-tile n is mapped to channel NT*j + n,
+//   so a lane's B elements over the NT n-tiles are NT consecutive floats of its neighbour's row: one 16-byte load
+//   per 4 channels, four full 128-byte rows per warp instruction.
+// * Accumulators: NT x 4 registers per lane = kernel points {g, g+8} x channels [2*NT*t, 2*NT*(t+1)).
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split3(float x, unsigned& hi, unsigned& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+template <int NT, bool DEFORM>
+__global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1Params p) {
+  constexpr int K = 15;
+  static_assert(NT % 4 == 0, "one float4 per four n-tiles");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = p.n0 + blockIdx.x * kS1Warps + warp;
+  if (n >= p.n1) return;  // warp-uniform
+  const int qid = p.order ? p.order[n] : n;
+  // this lane's two kernel points (rigid: shared by all queries; deformable: Kp + offsets[query])
+  const int kA = g, kB = g + 8;
+  const bool validB = kB < K;
+  float kax = p.Kp[3 * kA], kay = p.Kp[3 * kA + 1], kaz = p.Kp[3 * kA + 2];
+  float kbx = validB ? p.Kp[3 * kB] : 0.f, kby = validB ? p.Kp[3 * kB + 1] : 0.f, kbz = validB ? p.Kp[3 * kB + 2] : 0.f;
+  if (DEFORM) {
+    const float* off = p.offsets + (size_t)qid * K * 3;
+    kax += off[3 * kA]; kay += off[3 * kA + 1]; kaz += off[3 * kA + 2];
+    if (validB) { kbx += off[3 * kB]; kby += off[3 * kB + 1]; kbz += off[3 * kB + 2]; }
+  }
+  const float qx = p.q[3 * (size_t)qid], qy = p.q[3 * (size_t)qid + 1], qz = p.q[3 * (size_t)qid + 2];
+  const int* row = p.idx + (size_t)qid * p.H;
+  const float ext2 = p.extent * p.extent;
+  const unsigned tmask = 0x11111111u << t;   // the 8 lanes that hold the same neighbours as this lane
+  int nn_count = 0;
+
+  auto weight = [&](float d2) -> float {
+    if (p.influence == D3F_INFLUENCE_LINEAR) return fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
+    if (p.influence == D3F_INFLUENCE_GAUSSIAN) return __expf(-d2 * p.gauss_inv);
+    return DEFORM ? (d2 < ext2 ? 1.f : 0.f) : 1.f;
+  };
+
+  constexpr int CCH = NT * 8;   // channels per pass
+  for (int c0 = 0; c0 < p.Cin; c0 += CCH) {
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    const float* fcol = p.feat + c0 + NT * g;
+
+    for (int h0 = 0; h0 < p.H; h0 += 8) {
+      const int ha = h0 + t, hb = h0 + t + 4;
+      int ida = ha < p.H ? row[ha] : p.Ns, idb = hb < p.H ? row[hb] : p.Ns;
+      if (ida < 0 || ida > p.Ns) ida = p.Ns;
+      if (idb < 0 || idb > p.Ns) idb = p.Ns;
+      const float4 spa = __ldg(&p.s4[ida]), spb = __ldg(&p.s4[idb]);
+      const bool reala = ida < p.Ns, realb = idb < p.Ns;
+      // feature rows in fragment layout (issued before the weight math: latency overlaps it). A register-
+      // pipelined variant (rows one step ahead) was measured SLOWER: occupancy (63 vs 93 regs) matters more.
+      float fa[NT], fb[NT];
+#pragma unroll
+      for (int v = 0; v < NT; v += 4) {
+        float4 x = reala ? __ldg(reinterpret_cast<const float4*>(fcol + (size_t)ida * p.Cin + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 y = realb ? __ldg(reinterpret_cast<const float4*>(fcol + (size_t)idb * p.Cin + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        fa[v] = x.x; fa[v + 1] = x.y; fa[v + 2] = x.z; fa[v + 3] = x.w;
+        fb[v] = y.x; fb[v + 1] = y.y; fb[v + 2] = y.z; fb[v + 3] = y.w;
+      }
+      // squared distances to this lane's two kernel points
+      const float rax = spa.x - qx, ray = spa.y - qy, raz = spa.z - qz;
+      const float rbx = spb.x - qx, rby = spb.y - qy, rbz = spb.z - qz;
+      float d_aA = (rax - kax) * (rax - kax) + (ray - kay) * (ray - kay) + (raz - kaz) * (raz - kaz);
+      float d_aB = (rax - kbx) * (rax - kbx) + (ray - kby) * (ray - kby) + (raz - kbz) * (raz - kbz);
+      float d_bA = (rbx - kax) * (rbx - kax) + (rby - kay) * (rby - kay) + (rbz - kaz) * (rbz - kaz);
+      float d_bB = (rbx - kbx) * (rbx - kbx) + (rby - kby) * (rby - kby) + (rbz - kbz) * (rbz - kbz);
+      float w_aA = weight(d_aA), w_aB = validB ? weight(d_aB) : 0.f;
+      float w_bA = weight(d_bA), w_bB = validB ? weight(d_bB) : 0.f;
+      if (p.closest) {
+        // arg-min over all 15 kernel points of each neighbour = reduction over the 8 lanes sharing t
+        float ma = d_aA, mb = d_bA;
+        int ia = kA, ib = kA;
+        if (validB && d_aB < ma) { ma = d_aB; ia = kB; }
+        if (validB && d_bB < mb) { mb = d_bB; ib = kB; }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          float oa = __shfl_xor_sync(0xffffffffu, ma, o), ob = __shfl_xor_sync(0xffffffffu, mb, o);
+          int ja = __shfl_xor_sync(0xffffffffu, ia, o), jb = __shfl_xor_sync(0xffffffffu, ib, o);
+          if (oa < ma || (oa == ma && ja < ia)) { ma = oa; ia = ja; }
+          if (ob < mb || (ob == mb && jb < ib)) { mb = ob; ib = jb; }
+        }
+        w_aA = ia == kA ? w_aA : 0.f; w_aB = ia == kB ? w_aB : 0.f;
+        w_bA = ib == kA ? w_bA : 0.f; w_bB = ib == kB ? w_bB : 0.f;
+      }
+      bool keepa = reala, keepb = realb;
+      if (DEFORM) {
+        // a neighbour is kept if ANY deformed kernel point has it in range (:435-451)
+        const unsigned ra = __ballot_sync(0xffffffffu, d_aA < ext2 || (validB && d_aB < ext2));
+        const unsigned rb = __ballot_sync(0xffffffffu, d_bA < ext2 || (validB && d_bB < ext2));
+        keepa = keepa && (ra & tmask) != 0;
+        keepb = keepb && (rb & tmask) != 0;
+      }
+      if (!keepa) { w_aA = 0.f; w_aB = 0.f; }
+      if (!keepb) { w_bA = 0.f; w_bB = 0.f; }
+      if (c0 == 0 && p.count_nn) {
+        // lanes 0..3 (g == 0) cover the eight neighbours of this step once
+        nn_count += __popc(__ballot_sync(0xffffffffu, spa.w > 0.f) & 0xFu) + __popc(__ballot_sync(0xffffffffu, spb.w > 0.f) & 0xFu);
+      }
+      // A fragment: a0 = (kA, nb a), a1 = (kB, nb a), a2 = (kA, nb b), a3 = (kB, nb b); 3xTF32 split
+      unsigned ah[4], al[4];
+      split3(w_aA, ah[0], al[0]);
+      split3(w_aB, ah[1], al[1]);
+      split3(w_bA, ah[2], al[2]);
+      split3(w_bB, ah[3], al[3]);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        unsigned bh0, bl0, bh1, bl1;
+        split3(fa[i], bh0, bl0);
+        split3(fb[i], bh1, bl1);
+        mma_tf32(acc[i], ah, bh0, bh1);
+        mma_tf32(acc[i], al, bh0, bh1);
+        mma_tf32(acc[i], ah, bl0, bl1);
+      }
+    }
+
+    // ---- write wf: rows kA (acc[.][0..1]) and kB (acc[.][2..3]), channels c0 + 2*NT*t + [0, 2*NT) -------------
+    float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c0 + 2 * NT * t;
+    const float modA = (DEFORM && p.modulations) ? p.modulations[(size_t)qid * K + kA] : 1.f;
+    const float modB = (DEFORM && p.modulations && validB) ? p.modulations[(size_t)qid * K + kB] : 1.f;
+#pragma unroll
+    for (int v = 0; v < NT; v += 4) {
+      *reinterpret_cast<float4*>(dst + (size_t)kA * p.Cin + v) =
+          make_float4(acc[v][0] * modA, acc[v + 1][0] * modA, acc[v + 2][0] * modA, acc[v + 3][0] * modA);
+      *reinterpret_cast<float4*>(dst + (size_t)kA * p.Cin + NT + v) =
+          make_float4(acc[v][1] * modA, acc[v + 1][1] * modA, acc[v + 2][1] * modA, acc[v + 3][1] * modA);
+      if (validB) {
+        *reinterpret_cast<float4*>(dst + (size_t)kB * p.Cin + v) =
+            make_float4(acc[v][2] * modB, acc[v + 1][2] * modB, acc[v + 2][2] * modB, acc[v + 3][2] * modB);
+        *reinterpret_cast<float4*>(dst + (size_t)kB * p.Cin + NT + v) =
+            make_float4(acc[v][3] * modB, acc[v + 1][3] * modB, acc[v + 2][3] * modB, acc[v + 3][3] * modB);
+      }
+    }
+  }
+  if (p.inv_nn != nullptr && lane == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
+}
+
 template <int K, bool DEFORM>
 static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
   int nq = p.n1 - p.n0;
   bool al16 = (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.wf) & 15) == 0;
+#ifndef D3F_NO_MMA_STAGE1
+  if (K == 15 && al16 && (p.Cin == 32 || p.Cin == 64 || p.Cin % 128 == 0)) {
+    const int blocks = ceil_div(nq, kS1Warps);
+#if defined(D3F_MMA_NT4)
+    kpconv_stage1_mma_kernel<4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+#elif defined(D3F_MMA_NT8)
+    if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+    else kpconv_stage1_mma_kernel<8, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+#else
+    if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+    else if (p.Cin == 64) kpconv_stage1_mma_kernel<8, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+    else kpconv_stage1_mma_kernel<16, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+#endif
+    D3F_LAUNCH_CHECK("kpconv_stage1_mma_kernel");
+    return D3F_OK;
+  }
+#endif
 #ifdef D3F_STAGED   // measured slower than the direct-gather kernel on B200 (profiles/r1_notes.md); kept for experiments
   if (K == 15 && al16 && p.Cin % 128 == 0) return launch_stage1_v3<1, DEFORM>(p, stream);
   if (K == 15 && al16 && p.Cin == 64) return launch_stage1_v3<2, DEFORM>(p, stream);

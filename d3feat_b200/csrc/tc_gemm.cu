@@ -140,10 +140,11 @@ struct TcAcc {
   static constexpr int kCols = kAcc * BN;   // power of two <= 512
 };
 
-template <int BN>
+// ring depth = prefetch distance + 1. Skinny-K GEMMs (<= 4 k-chunks) take 2 stages so that two CTAs share an SM and
+// overlap each other's load / MMA / epilogue phases; long-K GEMMs take the deepest ring that fits (one CTA per SM).
+template <int BN, int STAGES>
 struct TcSmem {
-  // BN = 128: 3 x 64 KB stages, one CTA per SM. BN <= 64: 2 x (40..48 KB): two CTAs per SM overlap each other.
-  static constexpr int kStages = BN >= 128 ? 3 : 2;
+  static constexpr int kStages = STAGES;
   static constexpr int kABytes = kTcBM * 128;  // one image (hi or lo) of the A tile
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
@@ -153,13 +154,17 @@ struct TcSmem {
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
 
-template <int BN>
-__global__ void __launch_bounds__(kTcThreads, BN >= 128 ? 1 : 2)
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, (STAGES == 2 && BN <= 64) ? 2 : 1)
 tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ C, int M, int N, int K,
                int Kpad, int Npad, int chunks_per_split, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, STAGES>;
   constexpr int kStages = S::kStages;
   // 1024 B alignment: SWIZZLE_128B atoms are 8 rows x 128 B and the swizzle uses absolute address bits
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -194,64 +199,65 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < 4) {
-    // ===================== producers: global -> registers -> (hi, lo) -> swizzled shared memory ==========
-    // Software pipelined one chunk ahead: while chunk kt is split and stored, the A loads of chunk kt+1 are
-    // already in flight in registers and its (pre-split) B rows are in flight as cp.async into the next stage.
+    // ===================== producers: global --cp.async--> swizzled stage --(in-place hi/lo split)--> UMMA =====
+    // Every thread owns fixed 16-byte pieces of the stage (row = it*16 + rsub, chunk = tid & 7). It copies them
+    // asynchronously kStages-1 k-chunks ahead (A raw fp32 into the "hi" image, pre-split B into both images; rows
+    // beyond M / K are zero-filled), and when ITS OWN copy group of chunk kt has landed (cp.async.wait_group is
+    // per thread, so no extra barrier) it splits its A pieces in place: hi overwrites the raw value, lo goes to the
+    // second image. No register staging: the number of loads in flight is bounded by the stage ring only.
     const int chunk = tid & 7;      // 16-byte chunk inside the 128-byte row
     const int rsub = tid >> 3;      // 0..15: row inside a 16-row slab
     const float* Bhi = Bp;
     const float* Blo = Bp + (size_t)Npad * Kpad;
-    float4 a_cur[kTcBM / 16];
-    auto issue_chunk = [&](int kt, float4 (&a)[kTcBM / 16]) {
+    auto issue_chunk = [&](int kt) {
       const int s = kt % kStages;
       const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
       mbar_wait(smem_u32(&bars[kStages + s]), ph ^ 1u);      // stage free (its MMAs retired)
       uint8_t* st = smem + s * S::kStageBytes;
       const int k0 = (kt0 + kt) * kTcBK + chunk * 4;
 #pragma unroll
+      for (int it = 0; it < kTcBM / 16; ++it) {
+        const int row = it * 16 + rsub;
+        const int gm = m0 + row;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        const bool ok = gm < M && k0 < K;
+        cp_async16_zfill(smem_u32(st + off), A + (size_t)(ok ? gm : 0) * K + (ok ? k0 : 0), ok);
+      }
+#pragma unroll
       for (int it = 0; it < BN / 16; ++it) {
-        int row = it * 16 + rsub;
-        uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        size_t goff = (size_t)(n0 + row) * Kpad + k0;
+        const int row = it * 16 + rsub;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        const size_t goff = (size_t)(n0 + row) * Kpad + k0;
         cp_async16(smem_u32(st + 2 * S::kABytes + off), Bhi + goff);
         cp_async16(smem_u32(st + 2 * S::kABytes + S::kBBytes + off), Blo + goff);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-#pragma unroll
-      for (int it = 0; it < kTcBM / 16; ++it) {
-        int row = it * 16 + rsub;
-        int gm = m0 + row;
-        a[it] = (gm < M && k0 < K) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * K + k0))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
     };
-    issue_chunk(0, a_cur);
+    for (int i = 0; i < kStages - 1; ++i) {
+      if (i < nk) issue_chunk(i);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     for (int kt = 0; kt < nk; ++kt) {
       const int s = kt % kStages;
       uint8_t* st = smem + s * S::kStageBytes;
-      float4 a_next[kTcBM / 16];
-      const bool more = kt + 1 < nk;
-      if (more) issue_chunk(kt + 1, a_next);
+      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");   // this thread's pieces of chunk kt landed
 #pragma unroll
       for (int it = 0; it < kTcBM / 16; ++it) {
-        int row = it * 16 + rsub;
-        uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        const int row = it * 16 + rsub;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        const float4 x = *reinterpret_cast<const float4*>(st + off);
         float4 hi, lo;
-        split_tf32(a_cur[it].x, hi.x, lo.x);
-        split_tf32(a_cur[it].y, hi.y, lo.y);
-        split_tf32(a_cur[it].z, hi.z, lo.z);
-        split_tf32(a_cur[it].w, hi.w, lo.w);
+        split_tf32(x.x, hi.x, lo.x);
+        split_tf32(x.y, hi.y, lo.y);
+        split_tf32(x.z, hi.z, lo.z);
+        split_tf32(x.w, hi.w, lo.w);
         *reinterpret_cast<float4*>(st + off) = hi;
         *reinterpret_cast<float4*>(st + S::kABytes + off) = lo;
       }
-      if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");   // this thread's B rows of chunk kt landed
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&bars[s]));
-      if (more) {
-#pragma unroll
-        for (int it = 0; it < kTcBM / 16; ++it) a_cur[it] = a_next[it];
-      }
+      // refill the stage that MMA(kt-1) is about to release, kStages-1 chunks ahead
+      if (kt + kStages - 1 < nk) issue_chunk(kt + kStages - 1);
+      asm volatile("cp.async.commit_group;" ::: "memory");          // possibly empty: keeps the group count uniform
     }
 
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global ============
@@ -367,20 +373,20 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-template <int BN>
-static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
-                     cudaStream_t stream, int splits = 1, float* split_ws = nullptr) {
-  using S = TcSmem<BN>;
+template <int BN, int STAGES>
+static int launch_tc_s(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
+                       cudaStream_t stream, int splits, float* split_ws) {
+  using S = TcSmem<BN, STAGES>;
   static bool configured = false;   // idempotent attribute set; benign if two host threads race
   if (!configured) {
-    D3F_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    D3F_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
   int Kpad = tc_padded_k(K), Npad = tc_padded_n(N);
   const int nk = Kpad / kTcBK;
   if (splits <= 1) {
     dim3 grid(Npad / BN, ceil_div(M, kTcBM), 1);
-    tc_gemm_kernel<BN><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, C, M, N, K, Kpad, Npad, nk, ep);
+    tc_gemm_kernel<BN, STAGES><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, C, M, N, K, Kpad, Npad, nk, ep);
     D3F_LAUNCH_CHECK("tc_gemm_kernel");
     return D3F_OK;
   }
@@ -390,13 +396,24 @@ static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, in
   raw.rowscale = nullptr; raw.bn_scale = nullptr; raw.bn_shift = nullptr; raw.bias = nullptr; raw.residual = nullptr;
   raw.leaky_alpha = -1.f; raw.row_map = nullptr;
   dim3 grid(Npad / BN, ceil_div(M, kTcBM), splits);
-  tc_gemm_kernel<BN><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
+  tc_gemm_kernel<BN, STAGES><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
   D3F_LAUNCH_CHECK("tc_gemm_kernel");
   long long total = (long long)M * N;
   int blocks = (int)min((total + 255) / 256, (long long)kNumSMs * 8);
   splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(split_ws, splits, M, N, ep, C);
   D3F_LAUNCH_CHECK("splitk_reduce_kernel");
   return D3F_OK;
+}
+
+template <int BN>
+static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
+                     cudaStream_t stream, int splits = 1, float* split_ws = nullptr) {
+  const int nk_per_cta = ceil_div(tc_padded_k(K) / kTcBK, splits > 1 ? splits : 1);
+  const long long ctas = (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / BN) * (splits > 1 ? splits : 1);
+  // measured on B200 (scripts/gemm_probe.py): with more CTAs than SMs, two co-resident CTAs (2 stages each) beat one
+  // CTA with a deep ring; with few CTAs the deep ring wins
+  if (nk_per_cta <= 4 || (BN <= 64 && ctas > kNumSMs)) return launch_tc_s<BN, 2>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
+  return launch_tc_s<BN, (BN >= 128 ? 3 : 4)>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
 }
 
 bool tc_gemm_supported(const float* A, int K) {
