@@ -595,7 +595,9 @@ __device__ __forceinline__ void split3(float x, unsigned& hi, unsigned& lo) {
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-template <int NT, bool DEFORM>
+// FAST = the D3Feat configuration (KP_influence = linear, aggregation = sum) resolved at compile time; the
+// generic instantiation keeps the runtime switches for constant / gaussian / closest.
+template <int NT, bool DEFORM, bool FAST>
 __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1Params p) {
   constexpr int K = 15;
   static_assert(NT % 4 == 0, "one float4 per four n-tiles");
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1
   int nn_count = 0;
 
   auto weight = [&](float d2) -> float {
-    if (p.influence == D3F_INFLUENCE_LINEAR) return fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
+    if (FAST || p.influence == D3F_INFLUENCE_LINEAR) return fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
     if (p.influence == D3F_INFLUENCE_GAUSSIAN) return __expf(-d2 * p.gauss_inv);
     return DEFORM ? (d2 < ext2 ? 1.f : 0.f) : 1.f;
   };
@@ -659,7 +661,7 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1
       float d_bB = (rbx - kbx) * (rbx - kbx) + (rby - kby) * (rby - kby) + (rbz - kbz) * (rbz - kbz);
       float w_aA = weight(d_aA), w_aB = validB ? weight(d_aB) : 0.f;
       float w_bA = weight(d_bA), w_bB = validB ? weight(d_bB) : 0.f;
-      if (p.closest) {
+      if (!FAST && p.closest) {
         // arg-min over all 15 kernel points of each neighbour = reduction over the 8 lanes sharing t
         float ma = d_aA, mb = d_bA;
         int ia = kA, ib = kA;
@@ -734,15 +736,17 @@ static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
 #ifndef D3F_NO_MMA_STAGE1
   if (K == 15 && al16 && (p.Cin == 32 || p.Cin == 64 || p.Cin % 128 == 0)) {
     const int blocks = ceil_div(nq, kS1Warps);
-#if defined(D3F_MMA_NT4)
-    kpconv_stage1_mma_kernel<4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-#elif defined(D3F_MMA_NT8)
-    if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-    else kpconv_stage1_mma_kernel<8, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-#else
-    if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-    else if (p.Cin == 64) kpconv_stage1_mma_kernel<8, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-    else kpconv_stage1_mma_kernel<16, DEFORM><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+#if 1
+    const bool fast = p.influence == D3F_INFLUENCE_LINEAR && !p.closest;
+    if (fast) {
+      if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM, true><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else if (p.Cin == 64) kpconv_stage1_mma_kernel<8, DEFORM, true><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else kpconv_stage1_mma_kernel<16, DEFORM, true><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+    } else {
+      if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM, false><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else if (p.Cin == 64) kpconv_stage1_mma_kernel<8, DEFORM, false><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else kpconv_stage1_mma_kernel<16, DEFORM, false><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+    }
 #endif
     D3F_LAUNCH_CHECK("kpconv_stage1_mma_kernel");
     return D3F_OK;
@@ -851,11 +855,34 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
   }
 }
 
-// queries per chunk: keep the wf chunk (K*Cin floats per query) around 48 MB so it is produced and
+// Auxiliary stream + events for the chunk pipeline. Thread-local (one set per host thread), created lazily for the
+// current device: the library stays re-entrant across host threads, nothing is shared between them.
+struct AuxStream {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t s1_done[2] = {nullptr, nullptr};
+  cudaEvent_t gemm_done[2] = {nullptr, nullptr};
+};
+static AuxStream* aux_stream() {
+  static thread_local AuxStream a;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (a.stream != nullptr && a.device == dev) return &a;
+  if (a.stream != nullptr) return nullptr;   // a second device from the same thread: run un-overlapped
+  if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) { a.stream = nullptr; return nullptr; }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&a.s1_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&a.gemm_done[i], cudaEventDisableTiming);
+  }
+  a.device = dev;
+  return &a;
+}
+
+// queries per chunk: keep the wf chunk (K*Cin floats per query) around 40 MB (two buffers in flight) so it is produced and
 // consumed out of the 126 MB L2 instead of HBM
 static int chunk_queries(int K, int Cin) {
   long long per = (long long)K * Cin * 4;
-  long long n = (48ll << 20) / per;
+  long long n = (40ll << 20) / per;
   if (n < 1024) n = 1024;
   if (n > (1 << 20)) n = 1 << 20;
   return (int)(n / 128 * 128);
@@ -866,8 +893,8 @@ size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
   int chunk = chunk_queries(K, Cin);
   if (chunk > Nq) chunk = Nq > 0 ? Nq : 1;
   size_t b = 0;
-  b += align_up((size_t)chunk * K * Cin * sizeof(float), 256);
-  b += align_up((size_t)chunk * sizeof(float), 256);
+  b += 2 * align_up((size_t)chunk * K * Cin * sizeof(float), 256);   // wf is double-buffered (stage 1 / GEMM overlap)
+  b += 2 * align_up((size_t)chunk * sizeof(float), 256);
   b += align_up((size_t)(Ns + 1) * sizeof(float4), 256);
   b += align_up(tc_gemm_split_ws_floats(chunk, Cout, K * Cin) * sizeof(float), 256);
   return b + 1024;
@@ -896,8 +923,8 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   int chunk = chunk_queries(K, Cin);
   if (chunk > Nq) chunk = Nq;
   Carver cv(workspace, workspace_bytes);
-  float* wf = cv.take<float>((size_t)chunk * K * Cin);
-  float* inv_nn = cv.take<float>(chunk);
+  float* wf_buf[2] = {cv.take<float>((size_t)chunk * K * Cin), cv.take<float>((size_t)chunk * K * Cin)};
+  float* nn_buf[2] = {cv.take<float>(chunk), cv.take<float>(chunk)};
   float4* s4 = cv.take<float4>((size_t)Ns + 1);
   size_t split_floats = tc_gemm_split_ws_floats(chunk, Cout, K * Cin);
   float* split_ws = split_floats ? cv.take<float>(split_floats) : nullptr;
@@ -935,14 +962,30 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   p.influence = influence;
   p.closest = mode == D3F_MODE_CLOSEST;
   p.shadow = deform ? 1000.f : 1e6f;
-  p.wf = wf;
-  p.inv_nn = norm ? inv_nn : nullptr;
   p.order = query_order;
-  for (int n0 = 0; n0 < Nq; n0 += chunk) {
+  // Chunk pipeline: stage 1 of chunk i+1 (issue-bound on the SM pipes) runs on the caller's stream while the
+  // contraction of chunk i (latency-bound, tensor pipe mostly idle, ~9 us of fixed cost per launch) runs on an
+  // auxiliary stream; wf / inv_nn are double-buffered and the two streams are joined with events, so from the
+  // caller's point of view everything is still ordered on `stream`.
+  const int n_chunks = ceil_div(Nq, chunk);
+  AuxStream* aux = n_chunks > 1 ? aux_stream() : nullptr;
+  for (int ci = 0, n0 = 0; n0 < Nq; n0 += chunk, ++ci) {
+    const int b = ci & 1;
+    float* wf = wf_buf[b];
+    float* inv_nn = nn_buf[b];
+    p.wf = wf;
+    p.inv_nn = norm ? inv_nn : nullptr;
     p.n0 = n0;
     p.n1 = min(Nq, n0 + chunk);
+    if (aux && ci >= 2) D3F_CUDA(cudaStreamWaitEvent(stream, aux->gemm_done[b], 0));   // buffer b free again
     int rc = deform ? launch_stage1<15, true>(p, stream) : launch_stage1<15, false>(p, stream);
     if (rc) return rc;
+    cudaStream_t gs = stream;
+    if (aux) {
+      D3F_CUDA(cudaEventRecord(aux->s1_done[b], stream));
+      D3F_CUDA(cudaStreamWaitEvent(aux->stream, aux->s1_done[b], 0));
+      gs = aux->stream;
+    }
     Epilogue ep;
     ep.rowscale = norm ? inv_nn : nullptr;
     ep.bn_scale = bn_scale; ep.bn_shift = bn_shift; ep.bias = bias; ep.residual = nullptr;
@@ -951,11 +994,15 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     ep.row_map = query_order ? query_order + n0 : nullptr;
     float* cbase = query_order ? out : out + (size_t)n0 * Cout;
     if (W_packed != nullptr && tc_gemm_supported(wf, K * Cin))
-      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, stream,
-                   (p.n1 - n0 == chunk) ? split_ws : nullptr);
+      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, gs, n_chunks == 1 ? split_ws : nullptr);
     else
-      rc = gemm_f32(wf, W, cbase, p.n1 - n0, Cout, K * Cin, ep, stream);
+      rc = gemm_f32(wf, W, cbase, p.n1 - n0, Cout, K * Cin, ep, gs);
     if (rc) return rc;
+    if (aux) D3F_CUDA(cudaEventRecord(aux->gemm_done[b], aux->stream));
+  }
+  if (aux) {   // join: everything enqueued after this call on `stream` sees the complete output
+    D3F_CUDA(cudaStreamWaitEvent(stream, aux->gemm_done[0], 0));
+    if (n_chunks > 1) D3F_CUDA(cudaStreamWaitEvent(stream, aux->gemm_done[1], 0));
   }
   return D3F_OK;
 }

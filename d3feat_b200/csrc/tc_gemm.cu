@@ -100,17 +100,23 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// W[K,N] row-major -> packed[2][Npad][Kpad] (hi image, then lo image), K-major, zero padded.
+// W[K,N] row-major -> packed[Kpad/32][2][Npad][32]: for every 32-wide k-chunk a (hi, lo) pair of ready-made shared
+// memory images: row n holds the 32 k-values of output column n as 128 bytes whose 16-byte chunks are XOR-swizzled
+// with (n & 7) -- exactly the K-major SWIZZLE_128B layout the UMMA descriptor reads. A BN-row tile of a k-chunk is
+// therefore ONE contiguous block per image and is fetched by a single TMA bulk copy (cp.async.bulk).
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ W, int K, int N, int Kpad,
                                                           int Npad, float* __restrict__ packed) {
   long long total = (long long)Npad * Kpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int n = (int)(i / Kpad), k = (int)(i % Kpad);
+    int k = (int)(i / Npad), n = (int)(i % Npad);      // consecutive threads: consecutive n (coalesced reads of W)
     float x = (n < N && k < K) ? W[(size_t)k * N + n] : 0.f;
     float hi, lo;
     split_tf32(x, hi, lo);
-    packed[i] = hi;
-    packed[total + i] = lo;
+    int kc = k >> 5, kl = k & 31;
+    size_t slab = (size_t)kc * 2 * Npad * 32;
+    size_t off = (size_t)n * 32 + (size_t)((((kl >> 2) ^ (n & 7)) << 2) | (kl & 3));
+    packed[slab + off] = hi;
+    packed[slab + (size_t)Npad * 32 + off] = lo;
   }
 }
 
@@ -151,6 +157,14 @@ struct TcSmem {
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// TMA 1D bulk copy global -> shared, completing `bytes` on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
@@ -181,7 +195,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&bars[s]), kTcProducerThreads);
+      mbar_init(smem_u32(&bars[s]), kTcProducerThreads + 1);   // + the TMA issuer's arrive.expect_tx
       mbar_init(smem_u32(&bars[kStages + s]), 1);
     }
     mbar_init(smem_u32(&bars[2 * kStages]), 1);
@@ -207,8 +221,6 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
     // second image. No register staging: the number of loads in flight is bounded by the stage ring only.
     const int chunk = tid & 7;      // 16-byte chunk inside the 128-byte row
     const int rsub = tid >> 3;      // 0..15: row inside a 16-row slab
-    const float* Bhi = Bp;
-    const float* Blo = Bp + (size_t)Npad * Kpad;
     auto issue_chunk = [&](int kt) {
       const int s = kt % kStages;
       const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
@@ -223,13 +235,14 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
         const bool ok = gm < M && k0 < K;
         cp_async16_zfill(smem_u32(st + off), A + (size_t)(ok ? gm : 0) * K + (ok ? k0 : 0), ok);
       }
-#pragma unroll
-      for (int it = 0; it < BN / 16; ++it) {
-        const int row = it * 16 + rsub;
-        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        const size_t goff = (size_t)(n0 + row) * Kpad + k0;
-        cp_async16(smem_u32(st + 2 * S::kABytes + off), Bhi + goff);
-        cp_async16(smem_u32(st + 2 * S::kABytes + S::kBBytes + off), Blo + goff);
+      if (tid == 0) {
+        // B operand of this k-chunk: two contiguous pre-swizzled images (hi, lo) of BN rows x 128 B -> two TMA bulk
+        // copies that complete on the stage's "full" barrier
+        const uint32_t full = smem_u32(&bars[s]);
+        const float* slab = Bp + (size_t)(kt0 + kt) * 2 * Npad * 32 + (size_t)n0 * 32;
+        mbar_arrive_expect_tx(full, 2u * S::kBBytes);
+        tma_bulk_g2s(smem_u32(st + 2 * S::kABytes), slab, S::kBBytes, full);
+        tma_bulk_g2s(smem_u32(st + 2 * S::kABytes + S::kBBytes), slab + (size_t)Npad * 32, S::kBBytes, full);
       }
     };
     for (int i = 0; i < kStages - 1; ++i) {
