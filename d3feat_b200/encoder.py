@@ -56,3 +56,61 @@ class KPFCNN:
         use_dec = self.has_decoder if decoder is None else decoder
         desc = self.describe(inputs, F) if use_dec else None
         return dict(inputs=inputs, F=F, descriptors=desc)
+
+
+class BatchPipeline:
+    """Throughput mode: the input pyramid of batch i+1 is built on a second CUDA stream while the encoder of batch i
+    runs -- the overlap the reference gets from tf.data prefetch (its CPU pyramid runs ahead of the GPU model,
+    datasets/common.py:744-763). Usage:
+
+        pipe = BatchPipeline(enc)
+        pipe.prime(points0, lengths0, bbox0)            # pyramid of the first batch
+        for i in range(K):
+            out = pipe.step(points_next, lengths_next, bbox_next)   # encoder(i) || pyramid(i+1); returns F of batch i
+        pipe.drain()
+    """
+
+    def __init__(self, enc, decoder=False, post=None):
+        self.enc = enc
+        self.decoder = decoder
+        self.post = post                      # optional callable(inputs, F) run on the encoder stream (e.g. all-gather)
+        dev = enc.device
+        self.s_pyr = torch.cuda.Stream(device=dev)
+        self.s_enc = torch.cuda.Stream(device=dev)
+        self.ready = torch.cuda.Event()
+        self.pending = None
+        self.keep = []                        # keeps the previous batch's tensors alive until its kernels are done
+
+    def _build(self, points, lengths, bbox):
+        with torch.cuda.stream(self.s_pyr):
+            inputs = self.enc.build_inputs(points, lengths, bbox=bbox)
+            self.ready.record(self.s_pyr)
+        for v in inputs.values():             # the pyramid's tensors are consumed on the encoder stream
+            for t in (v if isinstance(v, (list, tuple)) else [v]):
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(self.s_enc)
+        return inputs
+
+    def prime(self, points, lengths, bbox=None):
+        self.pending = self._build(points, lengths, bbox)
+
+    def step(self, next_points=None, next_lengths=None, next_bbox=None, pre=None):
+        """Enqueue encoder(current batch) on the encoder stream, then build the pyramid of the next batch on the
+        pyramid stream (the host blocks only in that stream's size read-backs). Returns the current batch's result."""
+        inputs = self.pending
+        with torch.cuda.stream(self.s_enc):
+            self.s_enc.wait_event(self.ready)
+            if pre is not None:
+                pre()
+            F = self.enc.encode(inputs)
+            res = self.enc.describe(inputs, F) if self.decoder else F[-1]
+            if self.post is not None:
+                res = self.post(inputs, res)
+        self.keep = [inputs, F]
+        self.pending = self._build(next_points, next_lengths, next_bbox) if next_points is not None else None
+        return res
+
+    def drain(self):
+        self.s_pyr.synchronize()
+        self.s_enc.synchronize()
+        self.keep = []
