@@ -795,28 +795,36 @@ struct Cin1Params {
   float* out;
 };
 
+// 8 lanes per query (4 queries per warp): a lane walks neighbours sl, sl+8, ... and keeps the 15 partial sums
+// wf[k] in registers; a 3-step shuffle reduction inside the 8-lane group finishes wf, then the group's lanes split the
+// output channels with W[15, Cout] staged once per CTA in shared memory.
 __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
   constexpr int K = 15;
-  __shared__ float kp_s[K * 3];
+  extern __shared__ float c1_smem[];   // W[K*Cout] then Kp[K*3]
+  float* Ws = c1_smem;
+  float* kp_s = c1_smem + K * p.Cout;
+  for (int t = threadIdx.x; t < K * p.Cout; t += blockDim.x) Ws[t] = p.W[t];
   for (int t = threadIdx.x; t < K * 3; t += blockDim.x) kp_s[t] = p.Kp[t];
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (slot >= p.Nq) return;
-  const int n = p.order ? p.order[slot] : slot;
+  const int sub = lane >> 3, sl = lane & 7;
+  const int slot0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
+  if (slot0 >= p.Nq) return;  // warp-uniform
+  const int slot = slot0 + sub;
+  const bool qvalid = slot < p.Nq;
+  const int n = p.order ? p.order[qvalid ? slot : slot0] : (qvalid ? slot : slot0);
   const float qx = p.q[3 * (size_t)n], qy = p.q[3 * (size_t)n + 1], qz = p.q[3 * (size_t)n + 2];
   const int* row = p.idx + (size_t)n * p.H;
   float wf[K];
 #pragma unroll
   for (int k = 0; k < K; ++k) wf[k] = 0.f;
   int nn = 0;
-  for (int h0 = 0; h0 < p.H; h0 += 32) {
-    const int h = h0 + lane;
-    int id = (h < p.H) ? row[h] : p.Ns;
+  for (int h = sl; h < p.H; h += 8) {
+    int id = row[h];
     if (id < 0 || id > p.Ns) id = p.Ns;
     const float4 sp = __ldg(&p.s4[id]);   // (x, y, z, feature); entry Ns = shadow point with feature 0
     const float f = sp.w, rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
-    nn += __popc(__ballot_sync(0xffffffffu, f > 0.f));
+    nn += f > 0.f ? 1 : 0;
     float w[K];
     float dmin = 3.0e38f;
     int kmin = 0;
@@ -832,21 +840,21 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
       w[k] = wk;
     }
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      float t = (p.closest && k != kmin) ? 0.f : w[k] * f;   // f = 0 for shadow neighbours
-      wf[k] += t;
-    }
+    for (int k = 0; k < K; ++k) wf[k] += (p.closest && k != kmin) ? 0.f : w[k] * f;   // f = 0 for shadow neighbours
   }
+  // reduce over the 8 lanes of the query group
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
+  for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wf[k] += __shfl_xor_sync(0xffffffffu, wf[k], o);
+    for (int k = 0; k < K; ++k) wf[k] += __shfl_xor_sync(0xffffffffu, wf[k], o);
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
   }
+  if (!qvalid) return;
   const float inv_nn = p.normalize ? 1.f / (float)max(nn, 1) : 1.f;
-  for (int c = lane; c < p.Cout; c += 32) {
+  for (int c = sl; c < p.Cout; c += 8) {
     float y = 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) y = fmaf(wf[k], __ldg(p.W + (size_t)k * p.Cout + c), y);
+    for (int k = 0; k < K; ++k) y = fmaf(wf[k], Ws[k * p.Cout + c], y);
     y *= inv_nn;
     if (p.bn_scale) y = fmaf(y, p.bn_scale[c], p.bn_shift[c]);
     if (p.bias) y += p.bias[c];
@@ -947,7 +955,9 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     c1.bn_scale = bn_scale; c1.bn_shift = bn_shift; c1.bias = bias; c1.leaky_alpha = leaky_alpha;
     c1.order = query_order;
     c1.out = out;
-    kpconv_cin1_kernel<<<ceil_div(Nq * 32, 256), 256, 0, stream>>>(c1);
+    const size_t c1_smem = (size_t)(K * Cout + K * 3) * sizeof(float);
+    D3F_REQUIRE(c1_smem <= 48 * 1024, D3F_ERR_CAPACITY, "kpconv (Cin = 1): Cout=%d too wide for the first-layer kernel", Cout);
+    kpconv_cin1_kernel<<<ceil_div(ceil_div(Nq, 4) * 32, 256), 256, c1_smem, stream>>>(c1);
     D3F_LAUNCH_CHECK("kpconv_cin1_kernel");
     return D3F_OK;
   }

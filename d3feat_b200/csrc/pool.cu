@@ -74,7 +74,7 @@ int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, 
   if (N2 == 0) return D3F_OK;
   unsigned* colmin = (unsigned*)workspace;
   D3F_CUDA(cudaMemsetAsync(colmin, 0xff, sizeof(unsigned) * C, stream));
-  dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 8), 64));
+  dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 64), 2048));   // each thread reduces >= 8 rows before the atomics
   colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, C, colmin);
   D3F_LAUNCH_CHECK("colmin_kernel");
   int blocks = ceil_div(N2 * 32, 256);

@@ -1,0 +1,41 @@
+"""Small-size pass over every kernel of the library, meant to run under compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from d3feat_b200 import synth, tf_custom_ops as ops, cpp_subsampling, convolution_ops as co
+from d3feat_b200.encoder import KPFCNN
+dev = torch.device("cuda", 0)
+rng = np.random.default_rng(0)
+# native ops
+P = np.concatenate([synth.room_fragment(0, 1500), synth.room_fragment(1, 1100)], 0)
+L = np.array([1500, 1100], np.int32)
+tp, tl = torch.from_numpy(P).to(dev), torch.from_numpy(L).to(dev)
+nb = ops.batch_ordered_neighbors(tp, tp, tl, tl, 0.1)
+sp, sb = ops.batch_grid_subsampling(tp, tl, 0.06)
+ops.ordered_neighbors(tp[:300], tp[:300], 0.2)
+cpp_subsampling.compute(P[:1500], features=rng.normal(size=(1500, 3)).astype(np.float32), classes=rng.integers(0, 4, (1500,)).astype(np.int32), sampleDl=0.08)
+# dense rows -> generic path of the query kernel
+D = torch.from_numpy(rng.uniform(0, 0.15, (700, 3)).astype(np.float32)).to(dev)
+n700 = torch.tensor([700], dtype=torch.int32, device=dev)
+ops.batch_ordered_neighbors(D, D, n700, n700, 0.14, max_cols=32)
+# encoder + decoder (every KPConv variant incl. Cin=1, 32, 64, 128, 256, 512; TC GEMM all tile widths; split-K; pools)
+cfg = synth.Config()
+params = synth.make_params(cfg, 0)
+enc = KPFCNN(cfg, params, [30] * 5, device=dev)
+out = enc(np.concatenate([synth.room_fragment(2, 2500), synth.room_fragment(3, 2000)], 0), np.array([2500, 2000], np.int32), decoder=True)
+# deformable + generic influences / closest mode + CUDA-core fallback paths
+cfgd = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.3, first_features_dim=32, modulated=True)
+encd = KPFCNN(cfgd, synth.make_params(cfgd, 1), [24] * 5, device=dev)
+encd(synth.lidar_scan(0, 3000), np.array([3000], np.int32))
+q = torch.from_numpy(rng.uniform(0, 1, (400, 3)).astype(np.float32)).to(dev)
+idx = torch.from_numpy(rng.integers(0, 401, (400, 20)).astype(np.int32)).to(dev)
+for Cin, Cout in [(32, 32), (48, 40), (3, 8)]:
+    f = torch.randn(400, Cin, device=dev); W = torch.randn(15, Cin, Cout, device=dev); Kp = torch.randn(15, 3, device=dev) * 0.1
+    for infl in ("constant", "linear", "gaussian"):
+        for mode in ("sum", "closest"):
+            co.KPConv_ops(q, q, idx, f, Kp, W, 0.12, infl, mode)
+co.USE_TENSOR_CORES = False
+co.unary_convolution(torch.randn(300, 36, device=dev), torch.randn(36, 50, device=dev))
+co.KPConv_ops(q, q, idx, torch.randn(400, 32, device=dev), torch.randn(15, 3, device=dev) * 0.1, torch.randn(15, 32, 32, device=dev), 0.12, "linear", "sum")
+torch.cuda.synchronize()
+print("sanitize pass done")
