@@ -114,7 +114,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -340,11 +340,11 @@ def main():
         abytes = kpconv_algorithmic_bytes(Nq, H, 15, 32, 32)
         peak, peak_src = peaks()
         ach = abytes / (kms * 1e-3) / 1e9
-        # DRAM bytes of the op from the committed ncu capture (profiles/r1_v2_ncu_kpconv_metrics.txt): the stage-1
-        # kernel moves 14.6 MB per 26112-query chunk launch (cold caches); the gathered rows are L2 hits
-        n_chunks = -(-int(Nq) // 26112)
-        traffic = int(14.63e6 * n_chunks) if (args.fragments, args.points) == (8, 30000) else None
-        roof = dict(bound="hbm", kernel="kpconv level-0 32->32 (stage-1 gather + stage-2 contraction)", achieved=ach,
+        # DRAM bytes of the op from the committed ncu capture (profiles/r1_v3_ncu_metrics.txt): the stage-1 kernel
+        # moves 12.58 MB per 21760-query chunk launch (cold caches); the gathered rows themselves are L2 hits
+        n_chunks = -(-int(Nq) // 21760)
+        traffic = int(12.58e6 * n_chunks) if (args.fragments, args.points) == (8, 30000) else None
+        roof = dict(bound="hbm", kernel="kpconv level-0 32->32 (mma.sync stage-1 gather/correlation + tcgen05 contraction)", achieved=ach,
                     peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=abytes, ms_per_launch=kms, Nq=int(Nq), H=int(H))
 
