@@ -186,6 +186,16 @@ int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_st
   return l2_normalize(x, N, C, eps, out, (cudaStream_t)stream);
 }
 
+size_t d3f_detection_scores_workspace_bytes(int N, int B) { return detection_scores_workspace_bytes(N, B); }
+
+int d3f_detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N, int H, int D,
+                         float* out_scores, void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
+  D3F_REQUIRE(N == 0 || (feats && neighbors && lengths && out_scores && workspace), D3F_ERR_INVALID,
+              "d3f_detection_scores: null pointer");
+  return detection_scores(feats, neighbors, lengths, B, N, H, D, out_scores, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
 int d3f_affine_leaky(const float* x, int N, int C, const float* scale, const float* shift, const float* residual,
                      float leaky_alpha, float* out, d3f_stream_t stream) {
   D3F_REQUIRE(N == 0 || (x && out), D3F_ERR_INVALID, "d3f_affine_leaky: null pointer");

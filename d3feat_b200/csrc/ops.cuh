@@ -69,6 +69,9 @@ int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, 
 int closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C, float* out,
                  cudaStream_t stream);
 int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream_t stream);
+size_t detection_scores_workspace_bytes(int N, int B);
+int detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N, int H, int D,
+                     float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int affine_leaky(const float* x, int N, int C, const float* scale, const float* shift, const float* residual,
                  float alpha, float* out, cudaStream_t stream);
 

@@ -129,6 +129,92 @@ int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream
   return D3F_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Detection score of D3Feat (models/D3Feat.py:67-115), generalised from the reference's hard-coded pair of clouds to
+// B stacked clouds: per-cloud max normalisation, density-invariant saliency softplus(x - mean of the neighbours whose
+// feature-row sum is non-zero), channel-max ratio, max over channels.
+__global__ void __launch_bounds__(256)
+cloud_max_kernel(const float* __restrict__ x, int N, int D, const int* __restrict__ start, int B,
+                 unsigned* __restrict__ cloud_max_ord, unsigned char* __restrict__ nonzero) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  float m = -3.402823466e38f, s = 0.f;
+  for (int c = lane; c < D; c += 32) {
+    float v = x[(size_t)warp * D + c];
+    m = fmaxf(m, v);
+    s += v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+  }
+  if (lane == 0) {
+    atomicMax(&cloud_max_ord[batch_of(start, B, warp)], f2ord(m));
+    nonzero[warp] = s != 0.f ? 1 : 0;   // tf.count_nonzero of the neighbour's channel sum (:91-92)
+  }
+}
+
+__global__ void __launch_bounds__(256)
+detection_score_kernel(const float* __restrict__ x, const int* __restrict__ nb, int N, int H, int D,
+                       const int* __restrict__ start, int B, const unsigned* __restrict__ cloud_max_ord,
+                       const unsigned char* __restrict__ nonzero, float* __restrict__ score) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  // all neighbours of a point lie in its own cloud, so one scale serves the point and its neighbourhood
+  const float inv = 1.f / (ord2f(cloud_max_ord[batch_of(start, B, warp)]) + 1e-6f);
+  const int* row = nb + (size_t)warp * H;
+  int cnt = 0;
+  for (int h = 0; h < H; ++h) {
+    int id = row[h];
+    if (id >= 0 && id < N && nonzero[id]) ++cnt;
+  }
+  const float inv_cnt = 1.f / (float)max(cnt, 1);
+  float dmax = -3.402823466e38f;
+  for (int c = lane; c < D; c += 32) dmax = fmaxf(dmax, x[(size_t)warp * D + c] * inv);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  float best = -3.402823466e38f;
+  for (int c = lane; c < D; c += 32) {
+    const float f = x[(size_t)warp * D + c] * inv;
+    float mean = 0.f;
+    for (int h = 0; h < H; ++h) {
+      int id = row[h];
+      if (id >= 0 && id < N) mean += x[(size_t)id * D + c] * inv;   // the shadow row is zero
+    }
+    mean *= inv_cnt;
+    const float d = f - mean;
+    const float softplus = d > 20.f ? d : log1pf(expf(d));
+    best = fmaxf(best, softplus * (f / (1e-6f + dmax)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) score[warp] = best;
+}
+
+size_t detection_scores_workspace_bytes(int N, int B) {
+  return align_up(sizeof(int) * (size_t)(B + 1), 256) + align_up(sizeof(unsigned) * (size_t)B, 256) + align_up((size_t)N + 1, 256);
+}
+
+int detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N, int H, int D,
+                     float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  D3F_REQUIRE(B >= 1 && B <= kMaxBatch && N >= 0 && H >= 0 && D >= 1, D3F_ERR_INVALID, "detection_scores: bad shape");
+  D3F_REQUIRE(workspace_bytes >= detection_scores_workspace_bytes(N, B), D3F_ERR_WORKSPACE, "detection_scores: workspace too small");
+  if (N == 0) return D3F_OK;
+  Carver cv(workspace, workspace_bytes);
+  int* start = cv.take<int>(B + 1);
+  unsigned* cmax = cv.take<unsigned>(B);
+  unsigned char* nonzero = cv.take<unsigned char>((size_t)N + 1);
+  int rc = launch_batch_start(lengths, B, start, stream);
+  if (rc) return rc;
+  D3F_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned) * B, stream));
+  cloud_max_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(feats, N, D, start, B, cmax, nonzero);
+  D3F_LAUNCH_CHECK("cloud_max_kernel");
+  detection_score_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(feats, neighbors, N, H, D, start, B, cmax, nonzero, out_scores);
+  D3F_LAUNCH_CHECK("detection_score_kernel");
+  return D3F_OK;
+}
+
 __global__ void __launch_bounds__(256)
 affine_leaky_kernel(const float* __restrict__ x, long long total, int C, const float* __restrict__ scale,
                     const float* __restrict__ shift, const float* __restrict__ residual, float alpha,

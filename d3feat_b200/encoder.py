@@ -46,16 +46,18 @@ class KPFCNN:
         with use_params(self.store):
             return nb.assemble_CNN_blocks(inputs, self.config, 1.0)
 
-    def describe(self, inputs, F):
+    def describe(self, inputs, F, with_scores=False):
+        """Decoder -> descriptors [N,32]; with_scores=True -> (descriptors, detection scores [N,1]) -- the two arrays
+        tester.generate_descriptor dumps per fragment (utils/tester.py)."""
         with use_params(self.store):
-            return nb.assemble_FCNN_decoder(inputs, self.config, F, 1.0)
+            return nb.assemble_FCNN_decoder(inputs, self.config, F, 1.0, with_scores=with_scores)
 
     def __call__(self, stacked_points, stacked_lengths, features=None, bbox=None, decoder=None):
         inputs = self.build_inputs(stacked_points, stacked_lengths, features, bbox)
         F = self.encode(inputs)
         use_dec = self.has_decoder if decoder is None else decoder
-        desc = self.describe(inputs, F) if use_dec else None
-        return dict(inputs=inputs, F=F, descriptors=desc)
+        desc, scores = self.describe(inputs, F, with_scores=True) if use_dec else (None, None)
+        return dict(inputs=inputs, F=F, descriptors=desc, scores=scores)
 
 
 class BatchPipeline:

@@ -265,9 +265,32 @@ def assemble_CNN_blocks(inputs, config, dropout_prob):
     return F
 
 
-def assemble_FCNN_decoder(inputs, config, F, dropout_prob=1.0):
-    """models/D3Feat.py:15-65 -- decoder loop + l2-normalised 32-d descriptors (the detection-score branch,
-    :67-115, is the next row of the scope table)."""
+def detection_scores(features, neighbors, lengths):
+    """Detection branch of models/D3Feat.py:67-115 on the decoder output BEFORE l2 normalisation: per-cloud max
+    normalisation, softplus(x - mean over the non-zero neighbours), channel-max ratio, max over channels -> [N, 1].
+    The reference hard-codes two clouds per batch (anchor || positive); here any number of stacked clouds."""
+    x = features.contiguous()
+    nbr = neighbors.contiguous()
+    lens = _lib.i32(lengths, x.device)
+    N, D = int(x.shape[0]), int(x.shape[1])
+    B, H = int(lens.shape[0]), int(nbr.shape[1])
+    out = torch.empty((N, 1), dtype=torch.float32, device=x.device)
+    lib = _lib.lib()
+    ws = _lib.workspace(lib.d3f_detection_scores_workspace_bytes(N, B), x.device)
+    _lib.check(lib.d3f_detection_scores(_lib.ptr(x), _lib.ptr(nbr), _lib.ptr(lens), B, N, H, D, _lib.ptr(out),
+                                        _lib.ptr(ws), ws.numel(), _lib.stream()), "d3f_detection_scores")
+    return out
+
+
+def assemble_FCNN_blocks(inputs, config, dropout_prob=1.0):
+    """models/D3Feat.py:5-115 in one call: encoder + decoder -> (l2-normalised descriptors [N,32], scores [N,1])."""
+    F = assemble_CNN_blocks(inputs, config, dropout_prob)
+    return assemble_FCNN_decoder(inputs, config, F, dropout_prob, with_scores=True)
+
+
+def assemble_FCNN_decoder(inputs, config, F, dropout_prob=1.0, with_scores=False):
+    """models/D3Feat.py:15-65 -- decoder loop + l2-normalised 32-d descriptors; with_scores=True also runs the
+    detection branch (:67-115) and returns (descriptors, scores)."""
     features = F[-1]
     layer = config.num_layers - 1
     r = config.first_subsampling_dl * config.density_parameter * 2 ** layer
@@ -293,4 +316,6 @@ def assemble_FCNN_decoder(inputs, config, F, dropout_prob=1.0):
     out = torch.empty_like(features)
     _lib.check(_lib.lib().d3f_l2_normalize(_lib.ptr(features.contiguous()), features.shape[0], features.shape[1], 1e-10,
                                            _lib.ptr(out), _lib.stream()), "d3f_l2_normalize")
+    if with_scores:
+        return out, detection_scores(features, inputs["neighbors"][0], inputs["lengths"][0])
     return out

@@ -204,6 +204,14 @@ int d3f_closest_pool(const float* x, const int* inds, int N1, int N2, int ld_ind
 /* out[n,:] = x[n,:] * rsqrt(max(sum x^2, eps)) (tf.nn.l2_normalize, models/D3Feat.py:65) */
 int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream);
 
+/* Detection score of D3Feat (models/D3Feat.py:67-115) for B stacked clouds: feats[N,D] are the decoder outputs BEFORE
+ * l2 normalisation, neighbors[N,H] the level-0 conv neighbours (shadow index = N), lengths[B] the stack lengths.
+ * out_scores[N]. The reference hard-codes B = 2 (anchor || positive); the result is identical for B = 2. */
+size_t d3f_detection_scores_workspace_bytes(int N, int B);
+int d3f_detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N,
+                         int H, int D, float* out_scores, void* workspace, size_t workspace_bytes,
+                         d3f_stream_t stream);
+
 /* Stand-alone block epilogue for callers that do not use the fused forms
  * (models/network_blocks.py:149-165 batch_norm inference form, :185-186 leaky_relu, :368 residual add):
  * y = x*scale[c] + shift[c] (if scale) ; y += residual (if) ; LeakyReLU(leaky_alpha) if >= 0. */

@@ -279,9 +279,10 @@ class EncoderOracle:
             F.append(feats)
         return (F, trace) if return_all else F
 
-    def decoder(self, inputs, F):
+    def decoder(self, inputs, F, return_scores=False):
         """models/D3Feat.py:15-65: (nearest_upsample, concat, unary)* + last_unary + l2_normalize.
-        Variable scopes are 'uplayer_{layer}/{block}_{i}' (D3Feat.py:37)."""
+        Variable scopes are 'uplayer_{layer}/{block}_{i}' (D3Feat.py:37). return_scores=True also evaluates the
+        detection branch (:67-115) on the un-normalised features -> (descriptors, scores)."""
         cfg = self.cfg
         arch = list(cfg.architecture)
         start = next(i for i, b in enumerate(arch) if "upsample" in b)
@@ -305,7 +306,41 @@ class EncoderOracle:
                 feats = np.concatenate([feats, F[layer]], axis=1)          # D3Feat.py:63
         # tf.nn.l2_normalize(features, axis=1, epsilon=1e-10): x * rsqrt(max(sum(x^2), eps))
         norm = np.sqrt(np.maximum(np.sum(feats * feats, axis=1, keepdims=True), self.dt(1e-10)))
+        if return_scores:
+            return feats / norm, detection_scores(feats, inputs["neighbors"][0], inputs["lengths"][0])
         return feats / norm
+
+
+def detection_scores(features, neighbors, lengths):
+    """Detection branch, models/D3Feat.py:67-115, for any number of stacked clouds (the reference writes it out for
+    exactly two: first_pcd / second_pcd of in_batches).
+
+      :71      features ++ zero shadow row
+      :75-84   per cloud: features / (max over all points and channels of that cloud + 1e-6)
+      :87-93   neighbour rows gathered through neighbors[0]; neighbour_num = count_nonzero(sum over channels), >= 1;
+               mean = sum over neighbours / neighbour_num; local_max_score = softplus(features - mean)
+      :96-97   depth_wise_max_score = features / (1e-6 + max over channels)
+      :99-104  score = max over channels of the product; the shadow row is dropped.
+    """
+    x = np.asarray(features)
+    dt = x.dtype.type
+    N, D = x.shape
+    lengths = np.asarray(lengths, np.int64)
+    scaled = np.zeros((N + 1, D), x.dtype)
+    s = 0
+    for n in lengths:
+        if n > 0:
+            scaled[s:s + n] = x[s:s + n] / (x[s:s + n].max() + dt(1e-6))
+        s += n
+    nb = np.asarray(neighbors, np.int64)
+    nf = scaled[nb]                                           # [N, H, D]; shadow index N -> zero row
+    num = np.maximum(np.count_nonzero(nf.sum(axis=-1), axis=-1), 1).astype(x.dtype)[:, None]
+    mean = nf.sum(axis=1) / num
+    d = scaled[:N] - mean
+    softplus = np.where(d > 20, d, np.log1p(np.exp(np.minimum(d, dt(20)))))
+    dmax = scaled[:N].max(axis=1, keepdims=True)
+    score = (softplus * (scaled[:N] / (dt(1e-6) + dmax))).max(axis=1, keepdims=True)
+    return score.astype(x.dtype)
 
 
 # ----------------------------------------------------------------------------------------------------

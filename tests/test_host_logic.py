@@ -79,3 +79,25 @@ def test_oracle_pyramid_and_encoder_shapes():
     assert [f.shape[1] for f in F] == [32, 64, 128]
     assert F[2].shape[0] == inputs["points"][2].shape[0]
     assert all(np.isfinite(f).all() for f in F)
+
+
+def test_detection_score_restatement_against_scalar_loop():
+    """oracle/kpconv_np.detection_scores (vectorised) vs a literal per-point evaluation of models/D3Feat.py:67-115
+    for the reference's own batch shape (two clouds)."""
+    from oracle import kpconv_np as ok
+    rng = np.random.default_rng(0)
+    lengths = [40, 30]
+    N, D, H = 70, 8, 6
+    x = rng.normal(size=(N, D))
+    x[5] = 0.0
+    nb = np.concatenate([rng.integers(0, 40, (40, H)), rng.integers(40, 70, (30, H))]).astype(np.int64)
+    nb[rng.uniform(size=nb.shape) < 0.3] = N
+    got = ok.detection_scores(x, nb, lengths)
+    scale = np.concatenate([np.full(40, x[:40].max() + 1e-6), np.full(30, x[40:].max() + 1e-6)])
+    xs = np.concatenate([x / scale[:, None], np.zeros((1, D))])
+    for i in range(N):
+        rows = xs[nb[i]]
+        num = max(int(np.count_nonzero(rows.sum(axis=1))), 1)
+        local = np.log(1.0 + np.exp(xs[i] - rows.sum(axis=0) / num))
+        depth = xs[i] / (1e-6 + xs[i].max())
+        assert abs(got[i, 0] - (local * depth).max()) < 1e-12
