@@ -127,7 +127,7 @@ def room_fragment(seed, n_points=30000, dl=0.03):
 def lidar_scan(seed, n_points=120000, dl=0.30):
     """KITTI-shaped scan: ground plane + boxes seen by a 64-beam spinning lidar, voxelised at dl."""
     rng = np.random.default_rng(5000 + seed)
-    for n_az in (2600, 3600, 5200, 8000, 12000):
+    for n_az in (2600, 3600, 5200, 8000, 12000, 20000, 32000):
         az = np.linspace(0, 2 * np.pi, n_az, endpoint=False)
         el = np.deg2rad(np.linspace(-24.8, 2.0, 64))
         A, E = np.meshgrid(az, el)
