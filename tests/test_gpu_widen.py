@@ -124,3 +124,29 @@ def test_config3_full_size_deformable(cuda, monkeypatch):
         assert np.isfinite(a).all() and a.shape[0] == sizes[l]
         assert rel_err(a, b) < RTOL, "level %d" % l
         assert np.array_equal(a.view(np.uint32), c.view(np.uint32)), "level %d not reproducible" % l
+
+
+def test_released_weights_on_real_scan(cuda):
+    """First four blocks of the RELEASED 3DMatch model (trained weights, BN statistics and kernel points read from the
+    reference's snapshot by tf_checkpoint.py -> tests/golden/released_3dmatch_head.npz) on a crop of the reference's
+    real demo scan, two stacked clouds: GPU vs the float64 restatement."""
+    import os
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "released_3dmatch_head.npz"))
+    params = {k.replace("|", "/"): z[k] for k in z.files}
+    scan = np.load(os.path.join(gold, "subsampling_demo.npz"))
+    P, L = on.port_batch_subsampling(scan["points"], scan["lengths"], 0.03)
+    assert P.shape[0] > 1000
+    cfg = synth.Config(architecture=["simple", "resnetb", "resnetb_strided", "resnetb"])
+    limits = [38, 36]
+    out = KPFCNN(cfg, params, limits, device=cuda)(P, L)
+    inputs = {k: [x.cpu().numpy() for x in v] for k, v in out["inputs"].items() if k != "features"}
+    inputs["features"] = np.ones((P.shape[0], 1), np.float32)
+    F_ref, trace = ok.EncoderOracle(cfg, params, np.float64).encoder(inputs, return_all=True)
+    assert len(out["F"]) == len(F_ref) == 2
+    assert [f.shape[1] for f in F_ref] == [128, 256]
+    for l, (a, b) in enumerate(zip(out["F"], F_ref)):
+        assert np.abs(b).max() > 1e-3                       # trained weights produce a live signal
+        assert rel_err(a.cpu().numpy(), b) < RTOL, "level %d" % l
