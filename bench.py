@@ -286,11 +286,14 @@ def main():
         barrier()
         n0 = _lib.launch_count()
         t0 = time.perf_counter()
+        marks = []
         for _ in range(steps):
             one(True)
+            marks.append(time.perf_counter())
         pipe.drain()
         barrier()
         ms = (time.perf_counter() - t0) * 1000.0 / steps      # synchronised on both sides: device-bound wall time
+        step_marks.append([round((b - a) * 1000.0, 2) for a, b in zip([t0] + marks[:-1], marks)])
         launches = (_lib.launch_count() - n0) // max(steps, 1)
         if world > 1:
             tms = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -298,6 +301,7 @@ def main():
             ms = float(tms.item())
         return ms, launches
 
+    step_marks = []        # host-side time between consecutive pipeline steps (diagnostic: shows one-off stalls)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     seq_ms, _, _ = timed(step_resident, args.steps, max(args.warmup, 3))      # un-pipelined latency of one batch
     if args.no_pipeline:
@@ -308,7 +312,7 @@ def main():
         ms, launches = timed_pipelined(args.steps, max(args.warmup, 3), False)
         wall_ms = ms
         clocks = sampler.stop() if sampler else None
-        ms_e2e, _ = timed_pipelined(args.steps, 2, True)
+        ms_e2e, _ = timed_pipelined(args.steps, max(args.warmup, 3), True)
     total_points = n_points * world
     value = total_points / (ms / 1000.0)
     e2e_value = total_points / (ms_e2e / 1000.0)
@@ -363,6 +367,8 @@ def main():
         line["config"]["pipeline"] = ("one batch at a time" if args.no_pipeline else
                                       "two streams: pyramid(i+1) || encoder(i) (encoder.BatchPipeline)")
         line["single_batch_latency_ms"] = seq_ms
+        if step_marks:
+            line["pipeline_host_step_ms"] = dict(resident=step_marks[0], e2e=step_marks[-1])
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

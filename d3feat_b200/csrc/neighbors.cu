@@ -43,54 +43,59 @@ __device__ __forceinline__ int cell_coord(float v, float mn, float inv, int n) {
   return min(max(c, 0), n - 1);
 }
 
+// Grid build = counting sort by cell: (1) count points per cell, (2) exclusive scan -> cell_start (cell c owns
+// [cell_start[c], cell_start[c+1])), (3) scatter. The order of the points INSIDE a cell is whatever the atomics give;
+// no result depends on it (rows are emitted in (d2, index) order).
 __global__ void __launch_bounds__(256)
-support_key_kernel(const float* __restrict__ s, int Ns, const int* __restrict__ start, int B, NbGrid g,
-                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+cell_count_kernel(const float* __restrict__ s, int Ns, const int* __restrict__ start, int B, NbGrid g,
+                  uint32_t* __restrict__ cell_id, int* __restrict__ cell_cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ns) return;
   int b = batch_of(start, B, i);
   int cx = cell_coord(s[3 * (size_t)i], g.minx, g.inv_cell, g.nx);
   int cy = cell_coord(s[3 * (size_t)i + 1], g.miny, g.inv_cell, g.ny);
   int cz = cell_coord(s[3 * (size_t)i + 2], g.minz, g.inv_cell, g.nz);
-  keys[i] = (uint64_t)b * (uint64_t)g.ncells + ((uint64_t)cz * g.ny + cy) * g.nx + cx;
-  vals[i] = (uint32_t)i;
+  uint32_t c = (uint32_t)((long long)b * g.ncells + ((long long)cz * g.ny + cy) * g.nx + cx);
+  cell_id[i] = c;
+  atomicAdd(&cell_cnt[c], 1);
 }
 
-// sorted_pts[i] = (x, y, z, bits(index)); cell_start/cell_end from run boundaries (tables pre-zeroed)
+// sorted_pts[pos] = (x, y, z, bits(index)); cell_cnt is counted back down to zero
 __global__ void __launch_bounds__(256)
-grid_finalize_kernel(const float* __restrict__ s, const uint64_t* __restrict__ keys,
-                     const uint32_t* __restrict__ vals, int Ns, float4* __restrict__ sorted_pts,
-                     int* __restrict__ cell_start, int* __restrict__ cell_end) {
+cell_scatter_kernel(const float* __restrict__ s, int Ns, const uint32_t* __restrict__ cell_id,
+                    const int* __restrict__ cell_start, int* __restrict__ cell_cnt, float4* __restrict__ sorted_pts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ns) return;
-  uint32_t p = vals[i];
-  sorted_pts[i] = make_float4(s[3 * (size_t)p], s[3 * (size_t)p + 1], s[3 * (size_t)p + 2], __uint_as_float(p));
-  uint64_t k = keys[i];
-  if (i == 0 || keys[i - 1] != k) cell_start[k] = i;
-  if (i == Ns - 1 || keys[i + 1] != k) cell_end[k] = i + 1;
+  uint32_t c = cell_id[i];
+  int pos = cell_start[c] + atomicSub(&cell_cnt[c], 1) - 1;
+  sorted_pts[pos] = make_float4(s[3 * (size_t)i], s[3 * (size_t)i + 1], s[3 * (size_t)i + 2], __uint_as_float((uint32_t)i));
+}
+
+__global__ void __launch_bounds__(256)
+cell_order_kernel(const float4* __restrict__ sorted_pts, int Ns, int* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Ns) out[i] = (int)__float_as_uint(sorted_pts[i].w);
 }
 
 struct NbWs {
-  SortBuffers sort;
-  int* s_start;   // [B+1]
-  int* q_start;   // [B+1] (count / fill)
+  uint32_t* cell_id;  // [Ns] cell of every support
+  int* s_start;       // [B+1]
+  int* q_start;       // [B+1] (count / fill)
   float4* sorted_pts;
-  int* cell_start;
-  int* cell_end;
+  int* cell_start;    // [cells + 1]; the run of cell c is [cell_start[c], cell_start[c + 1])
+  int* cell_cnt;      // [cells + 1] build-time counters
+  int* scan_scratch;
 };
 
 static size_t carve_nb(Carver& cv, int Ns, int B, long long total_cells, NbWs& w) {
   int n = Ns > 0 ? Ns : 1;
-  w.sort.keys[0] = cv.take<uint64_t>(n);
-  w.sort.keys[1] = cv.take<uint64_t>(n);
-  w.sort.vals[0] = cv.take<uint32_t>(n);
-  w.sort.vals[1] = cv.take<uint32_t>(n);
-  w.sort.block_hist = cv.take<int>(256 * (size_t)sort_num_blocks(n));
+  w.cell_id = cv.take<uint32_t>(n);
   w.s_start = cv.take<int>(B + 1);
   w.q_start = cv.take<int>(B + 1);
   w.sorted_pts = cv.take<float4>(n);
   w.cell_start = cv.take<int>((size_t)total_cells + 1);
-  w.cell_end = cv.take<int>((size_t)total_cells + 1);
+  w.cell_cnt = cv.take<int>((size_t)total_cells + 1);
+  w.scan_scratch = cv.take<int>((size_t)scan_num_blocks((int)total_cells) + 1);
   return cv.off;
 }
 
@@ -120,19 +125,18 @@ int radius_neighbors_build(const float* supports, const int* s_batch_len, int B,
   NbWs w;
   carve_nb(cv, Ns, B, total, w);
   if (launch_batch_start(s_batch_len, B, w.s_start, stream)) return D3F_ERR_CUDA;
-  D3F_CUDA(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * ((size_t)total + 1), stream));
-  D3F_CUDA(cudaMemsetAsync(w.cell_end, 0, sizeof(int) * ((size_t)total + 1), stream));
-  if (Ns == 0) return D3F_OK;
-  support_key_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, w.s_start, B, g, w.sort.keys[0],
-                                                            w.sort.vals[0]);
-  D3F_LAUNCH_CHECK("support_key_kernel");
-  int bits = 1;
-  while (bits < 62 && (1ll << bits) < total) ++bits;
-  int cur = radix_sort_pairs(w.sort, Ns, bits, stream);
-  if (cur < 0) return cur;
-  grid_finalize_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, w.sort.keys[cur], w.sort.vals[cur], Ns,
-                                                              w.sorted_pts, w.cell_start, w.cell_end);
-  D3F_LAUNCH_CHECK("grid_finalize_kernel");
+  D3F_CUDA(cudaMemsetAsync(w.cell_cnt, 0, sizeof(int) * ((size_t)total + 1), stream));
+  if (Ns == 0) {
+    D3F_CUDA(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * ((size_t)total + 1), stream));
+    return D3F_OK;
+  }
+  cell_count_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, w.s_start, B, g, w.cell_id, w.cell_cnt);
+  D3F_LAUNCH_CHECK("cell_count_kernel");
+  if (exclusive_scan_i32(w.cell_cnt, w.cell_start, (int)total, w.cell_start + total, w.scan_scratch, stream))
+    return D3F_ERR_CUDA;
+  cell_scatter_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, w.cell_id, w.cell_start, w.cell_cnt,
+                                                             w.sorted_pts);
+  D3F_LAUNCH_CHECK("cell_scatter_kernel");
   return D3F_OK;
 }
 
@@ -148,10 +152,8 @@ int radius_neighbors_order(const void* workspace, int Ns, int B, float radius, c
   Carver cv(const_cast<void*>(workspace), ~(size_t)0);
   NbWs w;
   carve_nb(cv, Ns, B, total, w);
-  int bits = 1;
-  while (bits < 62 && (1ll << bits) < total) ++bits;
-  int cur = sort_num_passes(bits) & 1;
-  D3F_CUDA(cudaMemcpyAsync(out_order, w.sort.vals[cur], sizeof(int) * (size_t)Ns, cudaMemcpyDeviceToDevice, stream));
+  cell_order_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(w.sorted_pts, Ns, out_order);
+  D3F_LAUNCH_CHECK("cell_order_kernel");
   return D3F_OK;
 }
 
@@ -180,8 +182,7 @@ __device__ __forceinline__ float sq_dist_rn(float qx, float qy, float qz, float4
 template <bool FILL>
 __global__ void __launch_bounds__(kNbWarps * 32)
 radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ q_start, int B, NbGrid g,
-                    const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start,
-                    const int* __restrict__ cell_end, float r2, int cols, int pad_value,
+                    const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start, float r2, int cols, int pad_value,
                     int* __restrict__ counts, int* __restrict__ out_max, int* __restrict__ out_idx) {
   __shared__ int run_start[kNbWarps][9];
   __shared__ int run_prefix[kNbWarps][10];
@@ -202,14 +203,8 @@ radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__
     if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
       long long row = (long long)b * g.ncells + ((long long)zz * g.ny + yy) * g.nx;
       int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
-      int s = 0x7fffffff, e = 0;
-      for (int x = x0; x <= x1; ++x) {
-        int cs = cell_start[row + x], ce = cell_end[row + x];
-        if (ce > cs) {
-          s = min(s, cs);
-          e = max(e, ce);
-        }
-      }
+      // cells x0..x1 of one (y, z) row are adjacent in the table: one contiguous run of sorted_pts
+      int s = cell_start[row + x0], e = cell_start[row + x1 + 1];
       if (e > s) {
         rs = s;
         rl = e - s;
@@ -231,16 +226,21 @@ radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__
   const int T = run_prefix[warp][9];
 
   int n = 0;
+  // each lane walks the concatenated runs with stride 32, so its run index only moves forward
+  int r = 0, r_lo = 0, r_hi = run_prefix[warp][1], r_base = run_start[warp][0];
   for (int t0 = 0; t0 < T; t0 += 32) {
     int t = t0 + lane;
     bool hit = false;
     float d2 = 0.f;
     int sidx = 0;
     if (t < T) {
-      int r = 0;
-#pragma unroll
-      for (int k = 1; k < 9; ++k) r += (t >= run_prefix[warp][k]) ? 1 : 0;
-      float4 sp = sorted_pts[run_start[warp][r] + (t - run_prefix[warp][r])];
+      while (t >= r_hi) {   // t < T = run_prefix[9] bounds r at 8; empty runs are skipped
+        ++r;
+        r_lo = r_hi;
+        r_hi = run_prefix[warp][r + 1];
+        r_base = run_start[warp][r];
+      }
+      float4 sp = sorted_pts[r_base + (t - r_lo)];
       d2 = sq_dist_rn(qx, qy, qz, sp);
       sidx = (int)__float_as_uint(sp.w);
       hit = d2 < r2;
@@ -267,7 +267,49 @@ radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__
   if (out_max != nullptr && lane == 0) atomicMax(out_max, n);
   __syncwarp();
   int* row = out_idx + (size_t)qi * cols;
-  if (n <= kNbListCap) {
+  if (n <= 64) {
+    // the common case: bitonic sort of <= 64 packed (d2, idx) keys in registers, two per lane (elements lane and
+    // lane + 32). d2 >= +0, so the float's bit pattern orders like its value and the 64-bit key orders like
+    // (d2, idx) -- the same total order as hit_less.
+    const unsigned long long kInf = ~0ull;
+    unsigned long long a = kInf, b = kInf;
+    if (lane < n) a = ((unsigned long long)__float_as_uint(list[warp][lane].d2) << 32) | (unsigned)list[warp][lane].idx;
+    if (n <= 32) {
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          unsigned long long o = __shfl_xor_sync(0xffffffffu, a, j);
+          bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+          a = (keep_min == (o < a)) ? o : a;
+        }
+      }
+      if (lane < n && lane < cols) row[lane] = (int)(unsigned)a;
+    } else {
+      if (lane + 32 < n)
+        b = ((unsigned long long)__float_as_uint(list[warp][lane + 32].d2) << 32) | (unsigned)list[warp][lane + 32].idx;
+#pragma unroll
+      for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          if (j == 32) {   // partner of element lane is element lane + 32: same lane, ascending (k == 64)
+            unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+            a = lo;
+            b = hi;
+          } else {
+            unsigned long long oa = __shfl_xor_sync(0xffffffffu, a, j), ob = __shfl_xor_sync(0xffffffffu, b, j);
+            bool lower = (lane & j) == 0;
+            bool asc_a = (lane & k) == 0;                 // element index lane
+            bool asc_b = ((lane + 32) & k) == 0;          // element index lane + 32
+            a = ((lower == asc_a) == (oa < a)) ? oa : a;
+            b = ((lower == asc_b) == (ob < b)) ? ob : b;
+          }
+        }
+      }
+      if (lane < cols) row[lane] = (int)(unsigned)a;                      // n > 32: elements 0..31 are all hits
+      if (lane + 32 < n && lane + 32 < cols) row[lane + 32] = (int)(unsigned)b;
+    }
+  } else if (n <= kNbListCap) {
     // rank sort: rank = number of hits that precede in (d2, idx)
     for (int j = lane; j < n; j += 32) {
       float dj = list[warp][j].d2;
@@ -331,11 +373,11 @@ static int query_common(bool fill, const float* queries, const int* q_batch_len,
   int blocks = ceil_div(Nq, kNbWarps);
   if (fill) {
     radius_query_kernel<true><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, w.q_start, B, g, w.sorted_pts,
-                                                                    w.cell_start, w.cell_end, r2, cols, pad_value,
+                                                                    w.cell_start, r2, cols, pad_value,
                                                                     counts, out_max, out_idx);
   } else {
     radius_query_kernel<false><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, w.q_start, B, g, w.sorted_pts,
-                                                                     w.cell_start, w.cell_end, r2, 0, 0, counts,
+                                                                     w.cell_start, r2, 0, 0, counts,
                                                                      out_max, nullptr);
   }
   D3F_LAUNCH_CHECK("radius_query_kernel");

@@ -23,7 +23,7 @@ class KPFCNN:
         self.limits = [int(x) for x in neighborhood_limits]
         self.has_decoder = any("upsample" in b for b in config.architecture)
 
-    def build_inputs(self, stacked_points, stacked_lengths, features=None, bbox=None):
+    def build_inputs(self, stacked_points, stacked_lengths, features=None, bbox=None, buffers=None):
         pts = stacked_points
         if not torch.is_tensor(pts):
             pts = torch.as_tensor(np.ascontiguousarray(pts, np.float32))
@@ -32,7 +32,7 @@ class KPFCNN:
         if not torch.is_tensor(lens):
             lens = torch.as_tensor(np.ascontiguousarray(lens, np.int32))
         lens = lens.to(self.device, non_blocking=True)
-        inputs = pyramid.descriptor_input(self.config, pts, lens, self.limits, bbox=bbox)
+        inputs = pyramid.descriptor_input(self.config, pts, lens, self.limits, bbox=bbox, buffers=buffers)
         if features is None:
             # the 3DMatch generator feeds a constant-one feature (datasets/ThreeDMatch.py:316)
             features = torch.ones((pts.shape[0], self.config.in_features_dim), dtype=torch.float32, device=self.device)
@@ -82,11 +82,33 @@ class BatchPipeline:
         self.ready = torch.cuda.Event()
         self.pending = None
         self.keep = []                        # keeps the previous batch's tensors alive until its kernels are done
+        # Ring of pre-allocated pyramid slots: slot (i mod DEPTH) is rewritten by pyramid(i + DEPTH) only after the
+        # host has waited for encoder(i) (self.done), so at most DEPTH - 1 encoders are ever queued behind the host
+        # and steady-state batches allocate nothing for the pyramid.
+        self.slots = [None] * self.DEPTH
+        self.done = [None] * self.DEPTH
+        self.n_built = 0
+
+    DEPTH = 3
+
+    def _slot(self, n_points, n_clouds):
+        k = self.n_built % self.DEPTH
+        self.n_built += 1
+        if self.done[k] is not None:
+            self.done[k].synchronize()        # the encoder that read this slot DEPTH batches ago has finished
+        buf = self.slots[k]
+        if buf is None or not buf.fits(n_points, n_clouds, self.enc.limits):
+            buf = pyramid.PyramidBuffers(self.enc.config, self.enc.limits, int(n_points * 1.05) + 64, n_clouds,
+                                         self.enc.device)
+            self.slots[k] = buf
+        return k, buf
 
     def _build(self, points, lengths, bbox):
+        k, buf = self._slot(int(points.shape[0]), int(lengths.shape[0]))
         with torch.cuda.stream(self.s_pyr):
-            inputs = self.enc.build_inputs(points, lengths, bbox=bbox)
+            inputs = self.enc.build_inputs(points, lengths, bbox=bbox, buffers=buf)
             self.ready.record(self.s_pyr)
+        inputs["_slot"] = k
         for v in inputs.values():             # the pyramid's tensors are consumed on the encoder stream
             for t in (v if isinstance(v, (list, tuple)) else [v]):
                 if torch.is_tensor(t) and t.is_cuda:
@@ -108,6 +130,9 @@ class BatchPipeline:
             res = self.enc.describe(inputs, F) if self.decoder else F[-1]
             if self.post is not None:
                 res = self.post(inputs, res)
+            ev = torch.cuda.Event()
+            ev.record(self.s_enc)
+            self.done[inputs["_slot"]] = ev
         self.keep = [inputs, F]
         self.pending = self._build(next_points, next_lengths, next_bbox) if next_points is not None else None
         return res

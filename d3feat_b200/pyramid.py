@@ -89,7 +89,38 @@ def _ptr_array(tensors):
     return arr
 
 
-def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limits, bbox=None):
+class PyramidBuffers:
+    """Pre-allocated output matrices + workspace of one pyramid (a slot of BatchPipeline's ring): steady-state batches
+    then touch no allocator at all. Rows are sized for `capacity` level-0 points (every level gets the level-0
+    capacity: a subsampled level can never have more points than its parent)."""
+
+    def __init__(self, config, neighborhood_limits, capacity, n_clouds, device):
+        levels = _level_radii(config)
+        L = len(levels)
+        i32, f32 = torch.int32, torch.float32
+        self.capacity, self.n_clouds, self.device = int(capacity), int(n_clouds), device
+        self.limits = [int(neighborhood_limits[l]) for l in range(L)]
+        cap = max(self.capacity, 1)
+        self.pts = [None] + [torch.empty((cap, 3), dtype=f32, device=device) for _ in range(1, L)]
+        self.len = [None] + [torch.empty((n_clouds,), dtype=i32, device=device) for _ in range(1, L)]
+        self.nb = [torch.empty((cap, self.limits[l]), dtype=i32, device=device) if levels[l]["conv_r"] is not None
+                   else None for l in range(L)]
+        self.pool = [torch.empty((cap, self.limits[l]), dtype=i32, device=device) if levels[l]["dl"] is not None
+                     else None for l in range(L)]
+        self.up = [torch.empty((cap, self.limits[l]), dtype=i32, device=device) if levels[l]["dl"] is not None
+                   else None for l in range(L)]
+        self.ws = None
+
+    def fits(self, n_points, n_clouds, limits):
+        return n_points <= self.capacity and n_clouds == self.n_clouds and [int(x) for x in limits] == self.limits
+
+    def workspace(self, nbytes):
+        if self.ws is None or self.ws.numel() < nbytes:
+            self.ws = torch.empty((int(nbytes * 1.25) + 256,), dtype=torch.uint8, device=self.device)
+        return self.ws
+
+
+def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limits, bbox=None, buffers=None):
     """Returns the dict the blocks consume: points[L], neighbors[L], pools[L], upsamples[L], lengths[L]
     (placeholders of the reference's shapes at the last level, :1374-1377).
 
@@ -112,19 +143,27 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
     cap_arr = (C.c_int * L)(*cap)
     lib = _lib.lib()
     i32, f32 = torch.int32, torch.float32
-    out_pts = [None] + [torch.empty((cap[l], 3), dtype=f32, device=dev) for l in range(1, L)]
-    out_len = [None] + [torch.empty((B,), dtype=i32, device=dev) for l in range(1, L)]
-    lim = [int(neighborhood_limits[l]) for l in range(L)]
-    out_nb = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["conv_r"] is not None else None
-              for l in range(L)]
-    out_pool = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
-                for l in range(L)]
-    out_up = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
-              for l in range(L)]
+    if buffers is not None:
+        if not buffers.fits(N0, B, [neighborhood_limits[l] for l in range(L)]):
+            raise ValueError("pyramid: buffers (capacity %d, %d clouds) do not fit this batch (%d points, %d clouds)"
+                             % (buffers.capacity, buffers.n_clouds, N0, B))
+        cap = [max(buffers.capacity, 1)] * L
+        cap_arr = (C.c_int * L)(*cap)
+        out_pts, out_len, out_nb, out_pool, out_up = buffers.pts, buffers.len, buffers.nb, buffers.pool, buffers.up
+    else:
+        out_pts = [None] + [torch.empty((cap[l], 3), dtype=f32, device=dev) for l in range(1, L)]
+        out_len = [None] + [torch.empty((B,), dtype=i32, device=dev) for l in range(1, L)]
+        lim = [int(neighborhood_limits[l]) for l in range(L)]
+        out_nb = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["conv_r"] is not None else None
+                  for l in range(L)]
+        out_pool = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
+                    for l in range(L)]
+        out_up = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
+                  for l in range(L)]
     nbytes = lib.d3f_pyramid_workspace_bytes(B, C.byref(spec), cap_arr, bbp)
     if nbytes == 0:
         raise _lib.D3FError("pyramid: hash grid too large for bbox %s" % bb.tolist())
-    ws = _lib.workspace(nbytes, dev)
+    ws = buffers.workspace(nbytes) if buffers is not None else _lib.workspace(nbytes, dev)
     sizes = (C.c_int * L)()
     _lib.check(lib.d3f_pyramid_build(_lib.ptr(pts), _lib.ptr(lens), B, N0, C.byref(spec), bbp, _ptr_array(out_pts),
                                      _ptr_array(out_len), _ptr_array(out_nb), _ptr_array(out_pool),
