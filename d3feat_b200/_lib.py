@@ -41,6 +41,7 @@ SYMBOLS = [
     ("d3f_ind_max_pool", _I, [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     ("d3f_closest_pool", _I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     ("d3f_l2_normalize", _I, [_P, _I, _I, _F, _P, _P]),
+    ("d3f_unary_pair_forward", _I, [_P, _I, _P, _I, _P, _I, _I, _P, C.c_float, _P, _P]),
     ("d3f_detection_scores_workspace_bytes", _Z, [_I, _I]),
     ("d3f_detection_scores", _I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     ("d3f_affine_leaky", _I, [_P, _I, _I, _P, _P, _P, _F, _P, _P]),

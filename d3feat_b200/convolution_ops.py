@@ -80,6 +80,47 @@ def unary_convolution(features, K_values, *, epilogue=None, residual=None):
     return out
 
 
+_pair_cache = {}       # (id(w1), id(w2)) -> (refs, versions, packed image of the folded [w1*s1 ; w2*s2], shift1 + shift2)
+
+
+def unary_pair_convolution(x1, w1, affine1, x2, w2, affine2, alpha):
+    """leaky((x1 @ w1) * s1 + t1 + (x2 @ w2) * s2 + t2) as ONE GEMM over the concatenated K -- the conv3 + shortcut
+    + add + LeakyReLU tail of a resnetb block (models/network_blocks.py:343-368). affine = (scale, shift) of the
+    unary's inference batch norm. The scales are folded into the weights once per weight pair (float64), so neither
+    the shortcut tensor nor [x1 | x2] exists in memory. Falls back to two unary_convolution calls without the
+    tensor-core path or when the channel counts do not tile."""
+    x1, x2 = x1.contiguous(), x2.contiguous()
+    (s1, t1), (s2, t2) = affine1, affine2
+    N, C1 = x1.shape
+    C2 = int(x2.shape[1])
+    Cout = int(w1.shape[1])
+    if w1.shape[0] != C1 or w2.shape[0] != C2 or w2.shape[1] != Cout or x2.shape[0] != N:
+        raise ValueError("unary_pair_convolution: shapes %s@%s + %s@%s" % (tuple(x1.shape), tuple(w1.shape),
+                                                                             tuple(x2.shape), tuple(w2.shape)))
+    if not USE_TENSOR_CORES or C1 % 32 != 0 or C2 % 4 != 0:
+        shortcut = unary_convolution(x2, w2, epilogue=(s2, t2, None))
+        return unary_convolution(x1, w1, epilogue=(s1, t1, alpha), residual=shortcut)
+    key = (id(w1), id(w2))
+    hit = _pair_cache.get(key)
+    vers = (w1._version, w2._version, s1._version, s2._version, t1._version, t2._version)
+    if hit is None or hit[0][0]() is not w1 or hit[0][1]() is not w2 or hit[1] != vers:
+        folded = torch.cat([w1.double() * s1.double()[None, :], w2.double() * s2.double()[None, :]], 0).float()
+        shift = (t1.double() + t2.double()).float().contiguous()
+        L = _lib.lib()
+        packed = torch.empty((L.d3f_packed_weight_floats(C1 + C2, Cout),), dtype=torch.float32, device=w1.device)
+        _lib.check(L.d3f_pack_weight(_lib.ptr(folded.contiguous()), C1 + C2, Cout, _lib.ptr(packed), _lib.stream()),
+                   "d3f_pack_weight")
+        if hit is None:
+            weakref.finalize(w1, _pair_cache.pop, key, None)
+        hit = ((weakref.ref(w1), weakref.ref(w2)), vers, packed, shift)
+        _pair_cache[key] = hit
+    out = torch.empty((N, Cout), dtype=torch.float32, device=x1.device)
+    _lib.check(_lib.lib().d3f_unary_pair_forward(_lib.ptr(x1), C1, _lib.ptr(x2), C2, _lib.ptr(hit[2]), N, Cout,
+                                                 _lib.ptr(hit[3]), -1.0 if alpha is None else float(alpha),
+                                                 _lib.ptr(out), _lib.stream()), "d3f_unary_pair_forward")
+    return out
+
+
 def _check_enums(KP_influence, aggregation_mode):
     if KP_influence not in _INFLUENCE:
         raise ValueError("Unknown influence function type (config.KP_influence)")          # :224, :469

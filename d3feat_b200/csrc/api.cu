@@ -167,6 +167,24 @@ int d3f_unary_forward(const float* x, const float* W, const float* W_packed, int
   return gemm_f32(x, W, out, N, Cout, Cin, ep, (cudaStream_t)stream);
 }
 
+int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2, const float* W_packed, int N,
+                           int Cout, const float* shift, float leaky_alpha, float* out, d3f_stream_t stream) {
+  D3F_REQUIRE(N >= 0 && Cin1 >= 1 && Cin2 >= 1 && Cout >= 1, D3F_ERR_INVALID,
+              "d3f_unary_pair_forward: bad shape N=%d Cin=%d+%d Cout=%d", N, Cin1, Cin2, Cout);
+  D3F_REQUIRE(N == 0 || (x1 && x2 && W_packed && out), D3F_ERR_INVALID, "d3f_unary_pair_forward: null pointer");
+  D3F_REQUIRE(Cin1 % 32 == 0 && Cin2 % 4 == 0, D3F_ERR_INVALID,
+              "d3f_unary_pair_forward: Cin1 must be a multiple of 32 and Cin2 of 4 (got %d, %d)", Cin1, Cin2);
+  Epilogue ep;
+  ep.rowscale = nullptr;
+  ep.bn_scale = nullptr;
+  ep.bn_shift = nullptr;
+  ep.bias = shift;
+  ep.residual = nullptr;
+  ep.leaky_alpha = leaky_alpha;
+  ep.row_map = nullptr;
+  return tc_gemm(x1, W_packed, out, N, Cout, Cin1 + Cin2, ep, (cudaStream_t)stream, nullptr, x2, Cin1);
+}
+
 size_t d3f_ind_max_pool_workspace_bytes(int C) { return sizeof(unsigned) * (size_t)(C > 0 ? C : 1); }
 
 int d3f_ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,

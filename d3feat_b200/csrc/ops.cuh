@@ -21,7 +21,7 @@ size_t tc_packed_floats(int K, int N);
 int tc_pack_weight(const float* W, int K, int N, float* packed, cudaStream_t stream);
 bool tc_gemm_supported(const float* A, int K);
 int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
-            float* split_ws = nullptr);
+            float* split_ws = nullptr, const float* A2 = nullptr, int K1 = 0);
 int tc_gemm_splits(int M, int N, int K);
 size_t tc_gemm_split_ws_floats(int M, int N, int K);
 

@@ -12,6 +12,8 @@
 //   mbarrier ring overlaps the producers with the tensor pipe; tcgen05.commit releases stages / signals the epilogue.
 // * Epilogue: warps 0-3 read their 32 TMEM lanes (tcgen05.ld 32x32b), apply rowscale / BN / bias / residual /
 //   LeakyReLU and store rows straight to global memory.
+#include <stdlib.h>
+
 #include "ops.cuh"
 
 namespace d3f {
@@ -140,10 +142,13 @@ int tc_pack_weight(const float* W, int K, int N, float* packed, cudaStream_t str
 // ~ -1.1e-8 * K relative for all-positive data (scripts/tc_accuracy_probe.py). The k-chunks are therefore
 // rotated over kAcc independent TMEM accumulators (2 x 128 or 4 x 64 / 4 x 32 columns) that the epilogue adds
 // in registers with round-to-nearest: the truncation chain per accumulator is kAcc times shorter.
-template <int BN>
+// ACC = 0: the default rotation (2 x 128 or 4 x 64 / 4 x 32 columns: <= 256 TMEM columns per CTA, two CTAs fit in
+// the 512 columns). ACC = 1: a single accumulator for GEMMs of <= 4 k-chunks (K <= 128: bias < 1.5e-6), so that
+// four or five small CTAs share an SM.
+template <int BN, int ACC>
 struct TcAcc {
-  static constexpr int kAcc = BN >= 128 ? 2 : 4;   // <= 256 TMEM columns per CTA: two CTAs fit in the 512 columns
-  static constexpr int kCols = kAcc * BN;   // power of two <= 512
+  static constexpr int kAcc = ACC > 0 ? ACC : (BN >= 128 ? 2 : 4);
+  static constexpr int kCols = kAcc * BN;   // power of two, 32 <= kCols <= 512
 };
 
 // ring depth = prefetch distance + 1. Skinny-K GEMMs (<= 4 k-chunks) take 2 stages so that two CTAs share an SM and
@@ -173,10 +178,10 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads, (STAGES == 2 && BN <= 64) ? 2 : 1)
-tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float* __restrict__ C, int M, int N, int K,
-               int Kpad, int Npad, int chunks_per_split, Epilogue ep) {
+template <int BN, int STAGES, int ACC>
+__global__ void __launch_bounds__(kTcThreads, STAGES == 1 ? 4 : ((STAGES == 2 && BN <= 64) ? 2 : 1))
+tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1, const float* __restrict__ Bp,
+               float* __restrict__ C, int M, int N, int K, int Kpad, int Npad, int chunks_per_split, Epilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   using S = TcSmem<BN, STAGES>;
   constexpr int kStages = S::kStages;
@@ -203,7 +208,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TcAcc<BN>::kCols)
+                 "r"((uint32_t)TcAcc<BN, ACC>::kCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -226,14 +231,26 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
       const uint32_t ph = (uint32_t)(kt / kStages) & 1u;
       mbar_wait(smem_u32(&bars[kStages + s]), ph ^ 1u);      // stage free (its MMAs retired)
       uint8_t* st = smem + s * S::kStageBytes;
-      const int k0 = (kt0 + kt) * kTcBK + chunk * 4;
+      // the A operand is [A | A2] along K when A2 is given (K1 = columns of A, a multiple of the k-chunk): a whole
+      // k-chunk comes from one of the two row-major matrices
+      int k0 = (kt0 + kt) * kTcBK + chunk * 4;
+      const float* src = A;
+      int ld = K;
+      if (A2 != nullptr) {
+        ld = K1;
+        if (k0 >= K1) {
+          src = A2;
+          ld = K - K1;
+          k0 -= K1;
+        }
+      }
 #pragma unroll
       for (int it = 0; it < kTcBM / 16; ++it) {
         const int row = it * 16 + rsub;
         const int gm = m0 + row;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        const bool ok = gm < M && k0 < K;
-        cp_async16_zfill(smem_u32(st + off), A + (size_t)(ok ? gm : 0) * K + (ok ? k0 : 0), ok);
+        const bool ok = gm < M && k0 < ld;
+        cp_async16_zfill(smem_u32(st + off), src + (size_t)(ok ? gm : 0) * ld + (ok ? k0 : 0), ok);
       }
       if (tid == 0) {
         // B operand of this k-chunk: two contiguous pre-swizzled images (hi, lo) of BN rows x 128 B -> two TMA bulk
@@ -252,7 +269,15 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
     for (int kt = 0; kt < nk; ++kt) {
       const int s = kt % kStages;
       uint8_t* st = smem + s * S::kStageBytes;
-      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");   // this thread's pieces of chunk kt landed
+      if constexpr (kStages == 1) {
+        // one stage: copy, split, hand over; the next chunk's copy waits for this chunk's MMAs. The overlap comes
+        // from the other CTAs on the SM (four fit).
+        issue_chunk(kt);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages >= 2 ? kStages - 2 : 0) : "memory");   // chunk kt landed
+      }
 #pragma unroll
       for (int it = 0; it < kTcBM / 16; ++it) {
         const int row = it * 16 + rsub;
@@ -268,9 +293,11 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&bars[s]));
-      // refill the stage that MMA(kt-1) is about to release, kStages-1 chunks ahead
-      if (kt + kStages - 1 < nk) issue_chunk(kt + kStages - 1);
-      asm volatile("cp.async.commit_group;" ::: "memory");          // possibly empty: keeps the group count uniform
+      if constexpr (kStages > 1) {
+        // refill the stage that MMA(kt-1) is about to release, kStages-1 chunks ahead
+        if (kt + kStages - 1 < nk) issue_chunk(kt + kStages - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");        // possibly empty: keeps the group count uniform
+      }
     }
 
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced global ============
@@ -283,7 +310,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
     const int row = warp * 32 + lane;      // TMEM lane == tile row; warp w may only touch lanes [32w, 32w+32)
     const int gm = m0 + row;
     const float rs = (ep.rowscale != nullptr && gm < M) ? ep.rowscale[gm] : 1.f;
-    const int nacc = nk < TcAcc<BN>::kAcc ? nk : TcAcc<BN>::kAcc;
+    const int nacc = nk < TcAcc<BN, ACC>::kAcc ? nk : TcAcc<BN, ACC>::kAcc;
     float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     const int rows_here = min(32, M - (m0 + warp * 32));   // rows of this warp that exist (<= 0: none)
     const bool has_bn = ep.bn_scale != nullptr, has_bias = ep.bias != nullptr, has_res = ep.residual != nullptr;
@@ -347,8 +374,8 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
 #pragma unroll
         for (int j = 0; j < kTcBK / 8; ++j) {
           const uint64_t adv = (uint64_t)((j * 32) >> 4);   // +32 B per K = 8 step inside the swizzle atom
-          const uint32_t d = tmem_base + (uint32_t)((kt % TcAcc<BN>::kAcc) * BN);
-          umma_tf32(d, a_hi + adv, b_hi + adv, idesc, (kt >= TcAcc<BN>::kAcc || j != 0) ? 1u : 0u);
+          const uint32_t d = tmem_base + (uint32_t)((kt % TcAcc<BN, ACC>::kAcc) * BN);
+          umma_tf32(d, a_hi + adv, b_hi + adv, idesc, (kt >= TcAcc<BN, ACC>::kAcc || j != 0) ? 1u : 0u);
           umma_tf32(d, a_lo + adv, b_hi + adv, idesc, 1u);
           umma_tf32(d, a_hi + adv, b_lo + adv, idesc, 1u);
         }
@@ -363,7 +390,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ Bp, float*
   if (warp == 4) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"((uint32_t)TcAcc<BN>::kCols)
+                 "r"((uint32_t)TcAcc<BN, ACC>::kCols)
                  : "memory");
   }
 }
@@ -386,20 +413,20 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-template <int BN, int STAGES>
-static int launch_tc_s(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
-                       cudaStream_t stream, int splits, float* split_ws) {
+template <int BN, int STAGES, int ACC = 0>
+static int launch_tc_s(const float* A, const float* A2, int K1, const float* Bp, float* C, int M, int N, int K,
+                       const Epilogue& ep, cudaStream_t stream, int splits, float* split_ws) {
   using S = TcSmem<BN, STAGES>;
   static bool configured = false;   // idempotent attribute set; benign if two host threads race
   if (!configured) {
-    D3F_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    D3F_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<BN, STAGES, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     configured = true;
   }
   int Kpad = tc_padded_k(K), Npad = tc_padded_n(N);
   const int nk = Kpad / kTcBK;
   if (splits <= 1) {
     dim3 grid(Npad / BN, ceil_div(M, kTcBM), 1);
-    tc_gemm_kernel<BN, STAGES><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, C, M, N, K, Kpad, Npad, nk, ep);
+    tc_gemm_kernel<BN, STAGES, ACC><<<grid, kTcThreads, S::kTotal, stream>>>(A, A2, K1, Bp, C, M, N, K, Kpad, Npad, nk, ep);
     D3F_LAUNCH_CHECK("tc_gemm_kernel");
     return D3F_OK;
   }
@@ -409,7 +436,7 @@ static int launch_tc_s(const float* A, const float* Bp, float* C, int M, int N, 
   raw.rowscale = nullptr; raw.bn_scale = nullptr; raw.bn_shift = nullptr; raw.bias = nullptr; raw.residual = nullptr;
   raw.leaky_alpha = -1.f; raw.row_map = nullptr;
   dim3 grid(Npad / BN, ceil_div(M, kTcBM), splits);
-  tc_gemm_kernel<BN, STAGES><<<grid, kTcThreads, S::kTotal, stream>>>(A, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
+  tc_gemm_kernel<BN, STAGES, ACC><<<grid, kTcThreads, S::kTotal, stream>>>(A, A2, K1, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
   D3F_LAUNCH_CHECK("tc_gemm_kernel");
   long long total = (long long)M * N;
   int blocks = (int)min((total + 255) / 256, (long long)kNumSMs * 8);
@@ -418,15 +445,32 @@ static int launch_tc_s(const float* A, const float* Bp, float* C, int M, int N, 
   return D3F_OK;
 }
 
+// D3F_TC_SKINNY=0 disables the single-stage variant (A/B measurements); D3F_TC_SKINNY_CHUNKS caps its k-chunks
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+static bool force_deep_ring() {
+  static const bool off = env_int("D3F_TC_SKINNY", 1) == 0;
+  return off;
+}
+static const int kSkinnyChunks = [] { int c = env_int("D3F_TC_SKINNY_CHUNKS", 4); return c < 1 ? 1 : (c > 4 ? 4 : c); }();
+
 template <int BN>
-static int launch_tc(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep,
-                     cudaStream_t stream, int splits = 1, float* split_ws = nullptr) {
+static int launch_tc(const float* A, const float* A2, int K1, const float* Bp, float* C, int M, int N, int K,
+                     const Epilogue& ep, cudaStream_t stream, int splits = 1, float* split_ws = nullptr) {
   const int nk_per_cta = ceil_div(tc_padded_k(K) / kTcBK, splits > 1 ? splits : 1);
   const long long ctas = (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / BN) * (splits > 1 ? splits : 1);
   // measured on B200 (scripts/gemm_probe.py): with more CTAs than SMs, two co-resident CTAs (2 stages each) beat one
   // CTA with a deep ring; with few CTAs the deep ring wins
-  if (nk_per_cta <= 4 || (BN <= 64 && ctas > kNumSMs)) return launch_tc_s<BN, 2>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
-  return launch_tc_s<BN, (BN >= 128 ? 3 : 4)>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
+  // memory-bound skinny GEMMs with many output tiles (the level-0/1 unary convolutions): single-stage, single
+  // accumulator CTAs, four per SM -- their load / MMA / epilogue phases overlap across CTAs
+  if constexpr (BN <= 64) {
+    if (nk_per_cta <= kSkinnyChunks && splits <= 1 && ctas > 4ll * kNumSMs && !force_deep_ring())
+      return launch_tc_s<BN, 1, 1>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
+  }
+  if (nk_per_cta <= 4 || (BN <= 64 && ctas > kNumSMs)) return launch_tc_s<BN, 2>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
+  return launch_tc_s<BN, (BN >= 128 ? 3 : 4)>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
 }
 
 bool tc_gemm_supported(const float* A, int K) {
@@ -451,9 +495,12 @@ size_t tc_gemm_split_ws_floats(int M, int N, int K) {
 }
 
 int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
-            float* split_ws) {
+            float* split_ws, const float* A2, int K1) {
   if (M <= 0 || N <= 0) return D3F_OK;
   D3F_REQUIRE(tc_gemm_supported(A, K), D3F_ERR_INVALID, "tc_gemm: needs K %% 4 == 0 and 16-byte aligned A");
+  if (A2 != nullptr)
+    D3F_REQUIRE(K1 > 0 && K1 < K && K1 % kTcBK == 0 && tc_gemm_supported(A2, K - K1), D3F_ERR_INVALID,
+                "tc_gemm: split A operand needs K1 %% %d == 0 and a 16-byte aligned second matrix", kTcBK);
   int bn = tc_block_n(N);
   // skinny-K, huge-M GEMMs (the level-0/1 unary convolutions) are bound by per-CTA fixed costs and the C write:
   // 64-wide column tiles let two CTAs share an SM and overlap each other's load / MMA / epilogue phases. The packed
@@ -461,9 +508,9 @@ int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, cons
   if (bn == 128 && K <= 256 && M >= 8192) bn = 64;
   const int splits = split_ws != nullptr ? tc_gemm_splits(M, N, K) : 1;
   switch (bn) {
-    case 128: return launch_tc<128>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
-    case 64: return launch_tc<64>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
-    default: return launch_tc<32>(A, Bp, C, M, N, K, ep, stream, splits, split_ws);
+    case 128: return launch_tc<128>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
+    case 64: return launch_tc<64>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
+    default: return launch_tc<32>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
   }
 }
 

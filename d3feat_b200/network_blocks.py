@@ -176,14 +176,19 @@ def _resnetb(layer_ind, inputs, features, radius, fdim, config, training, stride
         else:
             x = conv(inputs["points"][layer_ind], inputs["points"][layer_ind], inputs["neighbors"][layer_ind], x, w,
                      radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind))
+    pair = None
     with variable_scope("shortcut"):
         shortcut = ind_max_pool(features, inputs["pools"][layer_ind]) if strided else features
         if int(shortcut.shape[1]) != 2 * fdim:
-            w = weight_variable([int(shortcut.shape[1]), 2 * fdim])
-            shortcut = conv_ops.unary_convolution(shortcut, w, epilogue=_bn_epilogue(config, None))
+            w_s = weight_variable([int(shortcut.shape[1]), 2 * fdim])
+            pair = (w_s, _bn_epilogue(config, None)[:2])
     with variable_scope("conv3"):
         w = weight_variable([int(x.shape[1]), 2 * fdim])
-        # conv3 + BN + shortcut add + LeakyReLU in one kernel (:343-368)
+        if pair is not None:
+            # conv3 + BN, shortcut unary + BN, add, LeakyReLU (:343-368) as one GEMM over the concatenated K
+            return conv_ops.unary_pair_convolution(x, w, _bn_epilogue(config, None)[:2], shortcut, pair[0], pair[1],
+                                                   0.2)
+        # conv3 + BN + shortcut add + LeakyReLU in one kernel
         return conv_ops.unary_convolution(x, w, epilogue=_bn_epilogue(config, 0.2), residual=shortcut)
 
 

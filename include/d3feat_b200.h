@@ -204,6 +204,14 @@ int d3f_closest_pool(const float* x, const int* inds, int N1, int N2, int ld_ind
 /* out[n,:] = x[n,:] * rsqrt(max(sum x^2, eps)) (tf.nn.l2_normalize, models/D3Feat.py:65) */
 int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream);
 
+/* Two unary convolutions that are summed -- the tail of every resnetb block (network_blocks.py:343-368: conv3 + BN,
+ * shortcut unary + BN, add, LeakyReLU) -- as ONE tensor-core GEMM over the concatenated K:
+ *   out = leaky([x1 | x2] @ W + shift),  W_packed = d3f_pack_weight of the [Cin1 + Cin2, Cout] matrix whose rows
+ * are the two weight matrices with their batch-norm scales folded in, shift = the sum of the two BN shifts.
+ * Neither the shortcut tensor nor the [x1 | x2] concatenation is ever materialised. Cin1 % 32 == 0, Cin2 % 4 == 0. */
+int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2, const float* W_packed, int N,
+                           int Cout, const float* shift, float leaky_alpha, float* out, d3f_stream_t stream);
+
 /* Detection score of D3Feat (models/D3Feat.py:67-115) for B stacked clouds: feats[N,D] are the decoder outputs BEFORE
  * l2 normalisation, neighbors[N,H] the level-0 conv neighbours (shadow index = N), lengths[B] the stack lengths.
  * out_scores[N]. The reference hard-codes B = 2 (anchor || positive); the result is identical for B = 2. */

@@ -69,3 +69,29 @@ def test_packed_weight_cache_tracks_tensor_identity(cuda, monkeypatch):
     w.mul_(2.0)                              # in-place update bumps _version -> re-pack
     b = co.unary_convolution(x, w)
     assert torch.allclose(b, 2 * a, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("N,C1,C2,Cout", [(5000, 32, 64, 128), (3001, 64, 128, 256), (700, 512, 1024, 2048),
+                                          (900, 48, 64, 96), (1, 32, 32, 32)])
+def test_unary_pair_convolution(cuda, N, C1, C2, Cout):
+    """conv3 + shortcut + add + LeakyReLU as one GEMM over the concatenated K (BN scales folded into the weights)
+    vs the float64 evaluation of the two separate unaries; (48, 64) does not tile and takes the two-call path."""
+    from d3feat_b200 import convolution_ops as co
+    rng = np.random.default_rng(N + C1)
+    x1 = rng.normal(size=(N, C1)).astype(np.float32)
+    x2 = rng.normal(size=(N, C2)).astype(np.float32)
+    w1 = (rng.normal(size=(C1, Cout)) / np.sqrt(C1)).astype(np.float32)
+    w2 = (rng.normal(size=(C2, Cout)) / np.sqrt(C2)).astype(np.float32)
+    s1, s2 = (rng.uniform(0.5, 1.5, Cout).astype(np.float32) for _ in range(2))
+    t1, t2 = (rng.normal(size=Cout).astype(np.float32) for _ in range(2))
+    tt = lambda a: torch.from_numpy(a).to(cuda)
+    W1, W2 = tt(w1), tt(w2)
+    args = (tt(x1), W1, (tt(s1), tt(t1)), tt(x2), W2, (tt(s2), tt(t2)), 0.2)
+    y = co.unary_pair_convolution(*args).cpu().numpy()
+    y_again = co.unary_pair_convolution(*args).cpu().numpy()          # second call: cached folded weights
+    ref = (x1.astype(np.float64) @ w1) * s1 + t1 + (x2.astype(np.float64) @ w2) * s2 + t2
+    ref = np.where(ref > 0, ref, 0.2 * ref)
+    assert np.abs(y - ref).max() <= 3e-5 * np.abs(ref).max()
+    assert np.array_equal(y, y_again)
+    with pytest.raises(ValueError):
+        co.unary_pair_convolution(tt(x1), W1, (tt(s1), tt(t1)), tt(x2[:, :-4]), W2, (tt(s2), tt(t2)), 0.2)
