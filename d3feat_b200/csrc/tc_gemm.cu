@@ -95,6 +95,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// explicit shared-window accesses: the aligned stage pointer is derived through integer arithmetic, so plain C++
+// dereferences compile to generic LD.E / ST.E; these keep the hot loops on LDS / STS
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // round-to-nearest TF32 split: hi has 10 explicit mantissa bits, lo = x - hi exactly
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
@@ -278,18 +297,27 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
       } else {
         asm volatile("cp.async.wait_group %0;" ::"n"(kStages >= 2 ? kStages - 2 : 0) : "memory");   // chunk kt landed
       }
+      // all of this thread's pieces are read before anything is written back: the loads are independent of the
+      // in-place stores (which the compiler could not prove), so the eight shared-memory round trips overlap
+      float4 x[kTcBM / 16];
+      const uint32_t st_s = smem_u32(st);
 #pragma unroll
       for (int it = 0; it < kTcBM / 16; ++it) {
         const int row = it * 16 + rsub;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-        const float4 x = *reinterpret_cast<const float4*>(st + off);
+        x[it] = lds128(st_s + off);
+      }
+#pragma unroll
+      for (int it = 0; it < kTcBM / 16; ++it) {
+        const int row = it * 16 + rsub;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         float4 hi, lo;
-        split_tf32(x.x, hi.x, lo.x);
-        split_tf32(x.y, hi.y, lo.y);
-        split_tf32(x.z, hi.z, lo.z);
-        split_tf32(x.w, hi.w, lo.w);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + S::kABytes + off) = lo;
+        split_tf32(x[it].x, hi.x, lo.x);
+        split_tf32(x[it].y, hi.y, lo.y);
+        split_tf32(x[it].z, hi.z, lo.z);
+        split_tf32(x[it].w, hi.w, lo.w);
+        sts128(st_s + off, hi);
+        sts128(st_s + S::kABytes + off, lo);
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&bars[s]));
@@ -311,7 +339,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
     const int gm = m0 + row;
     const float rs = (ep.rowscale != nullptr && gm < M) ? ep.rowscale[gm] : 1.f;
     const int nacc = nk < TcAcc<BN, ACC>::kAcc ? nk : TcAcc<BN, ACC>::kAcc;
-    float* tile = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+    const uint32_t tile = smem_u32(smem) + (uint32_t)warp * (32 * 33 * 4);
     const int rows_here = min(32, M - (m0 + warp * 32));   // rows of this warp that exist (<= 0: none)
     const bool has_bn = ep.bn_scale != nullptr, has_bias = ep.bias != nullptr, has_res = ep.residual != nullptr;
     const bool has_leaky = ep.leaky_alpha >= 0.f;
@@ -341,7 +369,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
         for (int j = 0; j < 32; ++j) v[j] += w[j];
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) tile[lane * 33 + j] = v[j] * rs;
+      for (int j = 0; j < 32; ++j) sts32(tile + (uint32_t)(lane * 33 + j) * 4u, v[j] * rs);
       __syncwarp();
       const float sc = (has_bn && col_ok) ? ep.bn_scale[gn] : 1.f;
       const float sh = (has_bn && col_ok) ? ep.bn_shift[gn] : 0.f;
@@ -350,7 +378,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
       for (int rr = 0; rr < 32; ++rr) {
         const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
         if (col_ok && rr < rows_here) {
-          float y = fmaf(tile[rr * 33 + lane], sc, sh) + bi;
+          float y = fmaf(lds32(tile + (uint32_t)(rr * 33 + lane) * 4u), sc, sh) + bi;
           if (has_res) y += res[rr];
           if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
           C[(size_t)orow * N + gn] = y;
