@@ -1004,7 +1004,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     ep.row_map = query_order ? query_order + n0 : nullptr;
     float* cbase = query_order ? out : out + (size_t)n0 * Cout;
     if (W_packed != nullptr && tc_gemm_supported(wf, K * Cin))
-      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, gs, n_chunks == 1 ? split_ws : nullptr);
+      rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, gs, split_ws);   // chunk GEMMs are serial on gs
     else
       rc = gemm_f32(wf, W, cbase, p.n1 - n0, Cout, K * Cin, ep, gs);
     if (rc) return rc;

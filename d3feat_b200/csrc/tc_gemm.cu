@@ -507,19 +507,39 @@ bool tc_gemm_supported(const float* A, int K) {
 
 // A[M,K] fp32 row-major, Bp = packed weight (tc_pack_weight), C[M,N]
 // split-K plan for GEMMs that cannot fill the GPU with output tiles: returns the number of K splits (1 = none)
+// Deterministic split-K plan for GEMMs whose output tiles cannot fill the GPU. The k-loop of a CTA is latency bound
+// (about a microsecond per k-chunk), so the cost of a plan is (waves of CTAs) x (k-chunks per CTA) plus the extra
+// pass of the reduction; the cheapest of s = 1..8 wins. Returns the number of K splits (1 = none).
 int tc_gemm_splits(int M, int N, int K) {
-  int bn = tc_block_n(N);
-  long long ctas = (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / bn);
-  int nk = tc_padded_k(K) / kTcBK;
-  if (ctas >= 96 || nk < 32) return 1;
-  int s = (int)((kNumSMs + ctas - 1) / ctas);
-  if (s > 8) s = 8;
-  if (s > nk / 8) s = nk / 8;
-  return s < 2 ? 1 : s;
+  const int bn = tc_block_n(N);
+  const long long ctas = (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / bn);
+  const int nk = tc_padded_k(K) / kTcBK;
+  if (ctas >= 96 || nk < 16) return 1;
+  int best = 1;
+  long long best_cost = (long long)ceil_div((int)ctas, kNumSMs) * nk * 8;   // in eighths of a k-chunk
+  for (int s = 2; s <= 8 && s <= nk / 4; ++s) {
+    const int cps = ceil_div(nk, s);
+    const int eff = ceil_div(nk, cps);   // splits actually launched
+    if (eff != s) continue;
+    long long cost = (long long)ceil_div((int)(ctas * s), kNumSMs) * cps * 8 + 40 + 6 * s;   // + reduce launch, traffic
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
 }
+// Workspace bound that holds for every M' <= M of the same GEMM family (the chunks of one KPConv share a buffer): the
+// planner only splits below 96 output tiles and never more than 8 ways, and a partial slab is at most one 128 x bn
+// tile per CTA, so 8 x min(tiles, 95) tiles always suffice.
 size_t tc_gemm_split_ws_floats(int M, int N, int K) {
-  int s = tc_gemm_splits(M, N, K);
-  return s > 1 ? (size_t)s * M * N : 0;
+  const int bn = tc_block_n(N);
+  const long long ctas = (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / bn);
+  const int nk = tc_padded_k(K) / kTcBK;
+  if (nk < 16) return 0;
+  // rows/cols covered by one CTA tile: 128 x bn. Worst case over all M' <= M: min(ctas, 95) tiles x 8 splits.
+  const long long tiles = ctas < 95 ? ctas : 95;
+  return (size_t)(8 * tiles * kTcBM * bn);
 }
 
 int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
