@@ -114,7 +114,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", os.environ.get("D3F_BENCH_LMS", "20")], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -282,6 +282,17 @@ def main():
         pipe.prime(src_p, src_l, src_bbox)
         for _ in range(warmup):
             one(False)
+        # untimed settling: a fresh process can see one-off stalls (allocator growth, the previous process's context
+        # still being torn down); keep warming up until five consecutive steps run within 1.5x of the fastest seen
+        best, calm = float("inf"), 0
+        for _ in range(40):
+            t_s = time.perf_counter()
+            one(False)
+            dt = time.perf_counter() - t_s
+            best = min(best, dt)
+            calm = calm + 1 if dt < 1.5 * best else 0
+            if calm >= 5:
+                break
         pipe.drain()
         barrier()
         n0 = _lib.launch_count()

@@ -185,7 +185,7 @@ int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2,
   return tc_gemm(x1, W_packed, out, N, Cout, Cin1 + Cin2, ep, (cudaStream_t)stream, nullptr, x2, Cin1);
 }
 
-size_t d3f_ind_max_pool_workspace_bytes(int C) { return sizeof(unsigned) * (size_t)(C > 0 ? C : 1); }
+size_t d3f_ind_max_pool_workspace_bytes(int C) { return sizeof(unsigned) * ((size_t)(C > 0 ? C : 1) + 1); }
 
 int d3f_ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,
                      size_t workspace_bytes, d3f_stream_t stream) {

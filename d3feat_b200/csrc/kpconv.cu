@@ -63,6 +63,32 @@ __global__ void __launch_bounds__(256) prep_supports_kernel(const float* __restr
   if (lane == 0) s4[warp] = make_float4(s[3 * (size_t)warp], s[3 * (size_t)warp + 1], s[3 * (size_t)warp + 2], w);
 }
 
+// mode 1 with Cin % 4 == 0: G lanes per support (G = 8 / 16 / 32 for Cin = 32 / 64 / >= 128) read the feature row as
+// float4, so a warp packs 32 / G supports per pass instead of one.
+template <int G>
+__global__ void __launch_bounds__(256) prep_supports_vec_kernel(const float* __restrict__ s,
+                                                                const float* __restrict__ feat, int Ns, int Cin,
+                                                                float shadow, float4* __restrict__ s4) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = t / G, gl = t % G;
+  float sum = 0.f;
+  if (row < Ns) {
+    const float4* fr = reinterpret_cast<const float4*>(feat + (size_t)row * Cin);
+    for (int c4 = gl; c4 < Cin / 4; c4 += G) {
+      float4 v = fr[c4];
+      sum += (v.x + v.y) + (v.z + v.w);
+    }
+  }
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (gl == 0) {
+    if (row < Ns)
+      s4[row] = make_float4(s[3 * (size_t)row], s[3 * (size_t)row + 1], s[3 * (size_t)row + 2], sum > 0.f ? 1.f : 0.f);
+    else if (row == Ns)
+      s4[Ns] = make_float4(shadow, shadow, shadow, 0.f);
+  }
+}
+
 template <int K, int VEC, bool DEFORM>
 __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Params p) {
   static_assert(K <= kKMax, "K too large");
@@ -939,8 +965,16 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   const bool norm = normalize != 0 && !deform;
   {
     int pmode = (Cin == 1 && !deform) ? 2 : (norm ? 1 : 0);
-    prep_supports_kernel<<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, pmode, deform ? 1000.f : 1e6f,
-                                                                            s4);
+    const float shadow = deform ? 1000.f : 1e6f;
+    const bool vec = pmode == 1 && Cin % 4 == 0 && Cin >= 32 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
+    if (vec && Cin < 64)
+      prep_supports_vec_kernel<8><<<ceil_div((Ns + 1) * 8, 256), 256, 0, stream>>>(s, feat, Ns, Cin, shadow, s4);
+    else if (vec && Cin < 128)
+      prep_supports_vec_kernel<16><<<ceil_div((Ns + 1) * 16, 256), 256, 0, stream>>>(s, feat, Ns, Cin, shadow, s4);
+    else if (vec)
+      prep_supports_vec_kernel<32><<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, shadow, s4);
+    else
+      prep_supports_kernel<<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, pmode, shadow, s4);
     D3F_LAUNCH_CHECK("prep_supports_kernel");
   }
   if (Cin == 1 && !deform) {

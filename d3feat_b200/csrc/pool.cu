@@ -6,10 +6,17 @@
 
 namespace d3f {
 
+// The shadow row of ind_max_pool is the column-wise minimum of x. A pooled row that has at least one real neighbour
+// never needs it (the minimum cannot exceed a real value), and the pyramid guarantees one (a cell's barycenter lies
+// within the pooling radius of one of the cell's points). So the pooling kernel runs first and raises a flag
+// (colmin_ord[C] = 0) for rows WITHOUT a real neighbour; the full-matrix reduction and the fix-up pass below exit
+// immediately while the flag is down, and produce the reference's result exactly when it is up.
+//
 // column-wise minimum via ordered-uint atomics; colmin_ord pre-set to 0xFFFFFFFF
 __global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x, int N, int C,
                                                      unsigned* __restrict__ colmin_ord) {
   __shared__ unsigned red[8][32];
+  if (colmin_ord[C] != 0u) return;   // no row asked for the shadow value
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
   unsigned m = 0xffffffffu;
@@ -28,7 +35,7 @@ __global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x
 template <int VEC>
 __global__ void __launch_bounds__(256)
 ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1, int N2, int H, int C,
-                    const unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
+                    unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N2) return;
   const int* row = inds + (size_t)warp * H;
@@ -36,13 +43,11 @@ ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, i
     float best[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) best[v] = -3.402823466e38f;
-    bool any_shadow = false;
+    bool any_real = false;
     for (int h = 0; h < H; ++h) {
       int id = row[h];
-      if (id < 0 || id >= N1) {
-        any_shadow = true;
-        continue;
-      }
+      if (id < 0 || id >= N1) continue;
+      any_real = true;
       const float* p = x + (size_t)id * C + c0;
       if (VEC == 4) {
         float4 t = *reinterpret_cast<const float4*>(p);
@@ -52,10 +57,9 @@ ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, i
         best[0] = fmaxf(best[0], *p);
       }
     }
-    if (any_shadow || H == 0) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v)
-        if (c0 + v < C) best[v] = fmaxf(best[v], ord2f(colmin_ord[c0 + v]));
+    if (!any_real) {   // every neighbour is the shadow: the row is the column minimum, filled in by the fix-up pass
+      if (lane == 0 && c0 == 0) colmin_ord[C] = 0u;
+      continue;
     }
     if (VEC == 4) {
       *reinterpret_cast<float4*>(out + (size_t)warp * C + c0) =
@@ -66,22 +70,42 @@ ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, i
   }
 }
 
+// rows without any real neighbour := column minimum (only runs its body when the pooling kernel raised the flag)
+__global__ void __launch_bounds__(256)
+ind_max_pool_fix_kernel(const int* __restrict__ inds, int N1, int N2, int H, int C,
+                        const unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
+  if (colmin_ord[C] != 0u) return;
+  const int lane = threadIdx.x & 31;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < N2; r += (gridDim.x * blockDim.x) >> 5) {
+    bool real = false;
+    for (int h = lane; h < H; h += 32) {
+      int id = inds[(size_t)r * H + h];
+      real = real || (id >= 0 && id < N1);
+    }
+    if (__any_sync(0xffffffffu, real)) continue;
+    for (int c = lane; c < C; c += 32) out[(size_t)r * C + c] = ord2f(colmin_ord[c]);
+  }
+}
+
 int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,
                  size_t workspace_bytes, cudaStream_t stream) {
   D3F_REQUIRE(N1 >= 1 && N2 >= 0 && H >= 0 && C >= 1, D3F_ERR_INVALID, "ind_max_pool: bad shape N1=%d N2=%d H=%d C=%d",
               N1, N2, H, C);
-  D3F_REQUIRE(workspace_bytes >= sizeof(unsigned) * (size_t)C, D3F_ERR_WORKSPACE, "ind_max_pool: workspace too small");
+  D3F_REQUIRE(workspace_bytes >= sizeof(unsigned) * ((size_t)C + 1), D3F_ERR_WORKSPACE,
+              "ind_max_pool: workspace too small");
   if (N2 == 0) return D3F_OK;
-  unsigned* colmin = (unsigned*)workspace;
-  D3F_CUDA(cudaMemsetAsync(colmin, 0xff, sizeof(unsigned) * C, stream));
-  dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 64), 2048));   // each thread reduces >= 8 rows before the atomics
-  colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, C, colmin);
-  D3F_LAUNCH_CHECK("colmin_kernel");
+  unsigned* colmin = (unsigned*)workspace;   // [C] ordered column minima + [1] flag (0xFFFFFFFF = not needed)
+  D3F_CUDA(cudaMemsetAsync(colmin, 0xff, sizeof(unsigned) * ((size_t)C + 1), stream));
   int blocks = ceil_div(N2 * 32, 256);
   bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   if (v4) ind_max_pool_kernel<4><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, H, C, colmin, out);
   else ind_max_pool_kernel<1><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, H, C, colmin, out);
   D3F_LAUNCH_CHECK("ind_max_pool_kernel");
+  dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 64), 4 * kNumSMs));
+  colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, C, colmin);
+  D3F_LAUNCH_CHECK("colmin_kernel");
+  ind_max_pool_fix_kernel<<<min(blocks, 4 * kNumSMs), 256, 0, stream>>>(inds, N1, N2, H, C, colmin, out);
+  D3F_LAUNCH_CHECK("ind_max_pool_fix_kernel");
   return D3F_OK;
 }
 

@@ -158,6 +158,10 @@ def test_pools_and_standalone_epilogue(cuda):
     inds[5] = 900                                           # an all-shadow row -> column minima
     out = nb.ind_max_pool(t(x, cuda), t(inds, cuda)).cpu().numpy()
     assert np.array_equal(out, ok.ind_max_pool(x, inds))    # max / min are exact
+    inds2 = inds.copy()
+    inds2[5, 3] = 7                                         # every row has a real neighbour: the lazy column-min
+    out = nb.ind_max_pool(t(x, cuda), t(inds2, cuda)).cpu().numpy()   # pass must not be needed, result unchanged
+    assert np.array_equal(out, ok.ind_max_pool(x, inds2))
     out = nb.closest_pool(t(x, cuda), t(inds, cuda)).cpu().numpy()
     assert np.array_equal(out, ok.closest_pool(x, inds))
     bn = {"s/batch_normalization/gamma": rng.uniform(0.5, 1.5, 128), "s/batch_normalization/beta": rng.normal(size=128),
