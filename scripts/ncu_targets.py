@@ -23,6 +23,7 @@ for it in range(3):
     if ONLY in ("", "kpconv"):
         co.KPConv_ops(q, q, idx, feat, Kp, W, 0.03, "linear", "sum")
     if ONLY in ("", "unary"):
-        co.unary_convolution(x32, w)
-        co.unary_convolution(x64, wsc)
+        co.unary_convolution(x32, w)                                  # 240000 x 32 -> 128 (skinny single-stage variant)
+        ones, zeros = torch.ones(128, device=dev), torch.zeros(128, device=dev)
+        co.unary_pair_convolution(x32, w, (ones, zeros), x64, wsc, (ones, zeros), 0.2)   # conv3 + shortcut, K = 32 + 64
 torch.cuda.synchronize()

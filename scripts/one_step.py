@@ -1,0 +1,18 @@
+"""One warm-up + N full steps (pyramid + encoder, one batch at a time) at the bench workload -- the short command the
+ncu launch list is taken from (bench.py itself runs ~8 steps' worth of launches, minutes under ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from d3feat_b200 import synth
+from d3feat_b200.encoder import KPFCNN
+dev = torch.device("cuda", 0)
+cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+enc = KPFCNN(cfg, synth.make_params(cfg, 0), [40] * 5, device=dev)
+clouds = [synth.room_fragment(f, 30000) for f in range(8)]
+P = np.concatenate(clouds, 0); L = np.array([c.shape[0] for c in clouds], np.int32)
+Pd, Ld = torch.from_numpy(P).to(dev), torch.from_numpy(L).to(dev)
+bbox = np.concatenate([P.min(0), P.max(0)]).astype(np.float32)
+for _ in range(1 + int(os.environ.get("STEPS", "1"))):
+    enc(Pd, Ld, bbox=bbox, decoder=False)
+    torch.cuda.synchronize()
+print("done")

@@ -34,6 +34,25 @@ for Cin, Cout in [(32, 32), (48, 40), (3, 8)]:
     for infl in ("constant", "linear", "gaussian"):
         for mode in ("sum", "closest"):
             co.KPConv_ops(q, q, idx, f, Kp, W, 0.12, infl, mode)
+# skinny single-stage GEMM variant (needs > 592 output tiles), pair GEMM, all-shadow pooled row, pipeline ring
+co.unary_convolution(torch.randn(80000, 32, device=dev), torch.randn(32, 64, device=dev))
+one = lambda c: (torch.ones(c, device=dev), torch.zeros(c, device=dev))
+co.unary_pair_convolution(torch.randn(5000, 32, device=dev), torch.randn(32, 128, device=dev), one(128),
+                          torch.randn(5000, 64, device=dev), torch.randn(64, 128, device=dev), one(128), 0.2)
+from d3feat_b200 import network_blocks as nbk
+pi = torch.from_numpy(rng.integers(0, 401, (100, 9)).astype(np.int32)).to(dev)
+pi[3] = 400
+nbk.ind_max_pool(torch.randn(400, 64, device=dev), pi)
+from d3feat_b200.encoder import BatchPipeline
+cfge = synth.Config(architecture=synth.ARCH_ENCODER)
+ence = KPFCNN(cfge, synth.make_params(cfge, 2), [30] * 5, device=dev)
+pipe = BatchPipeline(ence)
+bp, bl = np.concatenate([synth.room_fragment(4, 1500), synth.room_fragment(5, 1200)], 0), np.array([1500, 1200], np.int32)
+pipe.prime(bp, bl)
+for _ in range(4):
+    pipe.step(bp, bl)
+pipe.step(None, None)
+pipe.drain()
 co.USE_TENSOR_CORES = False
 co.unary_convolution(torch.randn(300, 36, device=dev), torch.randn(36, 50, device=dev))
 co.KPConv_ops(q, q, idx, torch.randn(400, 32, device=dev), torch.randn(15, 3, device=dev) * 0.1, torch.randn(15, 32, 32, device=dev), 0.12, "linear", "sum")
