@@ -12,7 +12,14 @@ clouds = [synth.room_fragment(f, 30000) for f in range(8)]
 P = np.concatenate(clouds, 0); L = np.array([c.shape[0] for c in clouds], np.int32)
 Pd, Ld = torch.from_numpy(P).to(dev), torch.from_numpy(L).to(dev)
 bbox = np.concatenate([P.min(0), P.max(0)]).astype(np.float32)
-for _ in range(1 + int(os.environ.get("STEPS", "1"))):
+# two warm-up steps (weight packing, BN folding, allocator), then the profiled ones between cudaProfilerStart/Stop:
+#   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv ... python scripts/one_step.py
+for _ in range(2):
+    enc(Pd, Ld, bbox=bbox, decoder=False)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for _ in range(int(os.environ.get("STEPS", "1"))):
     enc(Pd, Ld, bbox=bbox, decoder=False)
     torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("done")
