@@ -356,10 +356,11 @@ def main():
         abytes = kpconv_algorithmic_bytes(Nq, H, 15, 32, 32)
         peak, peak_src = peaks()
         ach = abytes / (kms * 1e-3) / 1e9
-        # DRAM bytes of the op from the committed ncu capture (profiles/r1_v3_ncu_metrics.txt): the stage-1 kernel
-        # moves 12.58 MB per 21760-query chunk launch (cold caches); the gathered rows themselves are L2 hits
+        # DRAM bytes of the op from the committed ncu capture (profiles/r1_v4_ncu_metrics.txt), per 21760-query chunk:
+        # stage-1 kernel 8.07 MB read + 0.33 MB written (the gathered rows are L2 hits), contraction 42.04 MB read
+        # (the chunk's wf -- ncu flushes L2 between kernels; back to back it is an L2 hit as well)
         n_chunks = -(-int(Nq) // 21760)
-        traffic = int(12.58e6 * n_chunks) if (args.fragments, args.points) == (8, 30000) else None
+        traffic = int((8.07e6 + 0.33e6 + 42.04e6) * n_chunks) if (args.fragments, args.points) == (8, 30000) else None
         roof = dict(bound="hbm", kernel="kpconv level-0 32->32 (mma.sync stage-1 gather/correlation + tcgen05 contraction)", achieved=ach,
                     peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
                     algorithmic_bytes_per_launch=abytes, ms_per_launch=kms, Nq=int(Nq), H=int(H))
