@@ -129,3 +129,41 @@ def test_keypoint_selection_and_writers(tmp_path):
     assert d.shape == (N, 32) and k.shape == (N, 3) and s.shape == (N, 1) and d.dtype == np.float32
     assert (np.diff(s[:, 0]) >= 0).all()                    # ascending: evaluate.py takes the LAST 250 rows
     assert np.array_equal(k[-1], pts[np.argmax(sc)]) and np.array_equal(d[-1], desc[np.argmax(sc)])
+
+
+@needs_ref
+def test_released_model_registers_the_demo_pair_through_the_restatement():
+    """Behavioural known answer for the TF-graph restatement (oracle/kpconv_np.py): with the RELEASED 3DMatch weights,
+    BN statistics and kernel points (read by tf_checkpoint.py) the numpy encoder + decoder + detector must produce
+    descriptors that register the reference's demo fragments (demo_registration.py flow); with the weights shuffled
+    inside each tensor the matches must collapse. scripts/oracle_released_demo.py is the full-size version
+    (2500 keypoints: 53 % inlier ratio, overlap 6 % -> 81 %, tests/golden/released_demo_summary.json)."""
+    import importlib.util
+    from scipy.spatial import cKDTree
+    from oracle import native as on
+    spec = importlib.util.spec_from_file_location(
+        "oracle_released_demo", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts",
+                                             "oracle_released_demo.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    if not on.have_ref():
+        on.build(ref=True)
+    cfg = io_utils.load_config(os.path.join(REF, "results", "Log_contraloss"))
+    params = ck.load_params(os.path.join(REF, "results", "Log_contraloss", "snapshots", "snap-54"))
+    clouds = []
+    for i in (0, 1):
+        raw = io_utils.read_ply_points(os.path.join(REF, "demo_data", "cloud_bin_%d.ply" % i))
+        clouds.append(on.ref_batch_subsampling(raw, np.array([raw.shape[0]], np.int32), cfg.first_subsampling_dl)[0])
+    limits = [37, 35, 36, 38, 38]                       # demo.calibrate(cfg, clouds), tests/golden/released_demo_summary.json
+    d, s = zip(*(demo.describe(cfg, params, limits, c) for c in clouds))
+    assert all(np.allclose(np.linalg.norm(x, axis=1), 1.0, atol=1e-4) for x in d)
+    kp = [np.argsort(x[:, 0])[-1500:] for x in s]
+    d0, d1 = d[0][kp[0]], d[1][kp[1]]
+    nn01 = cKDTree(d1).query(d0)[1]
+    mutual = np.nonzero(cKDTree(d0).query(d1)[1][nn01] == np.arange(d0.shape[0]))[0]
+    src, dst = clouds[0][kp[0]][mutual], clouds[1][kp[1]][nn01[mutual]]
+    r, t, inl = demo.ransac(src, dst, iters=3000)
+    assert mutual.size > 100 and inl.sum() / mutual.size > 0.3
+    before = np.mean(cKDTree(clouds[1]).query(clouds[0])[0] < 0.05)
+    after = np.mean(cKDTree(clouds[1]).query(clouds[0] @ r.T + t)[0] < 0.05)
+    assert before < 0.15 and after > 0.6
