@@ -1,5 +1,5 @@
 """GPU parity for the rows SURVEY.md §8(f) marks "next": the detection score that is dumped next to the descriptors,
-neighbourhood calibration, and the deformable KITTI-shaped configuration at its full size (BASELINE.json configs[3]).
+neighbourhood calibration, and the deformable KITTI-shaped configuration at its full size (BASELINE.json configs[2]).
 
 Tolerances as in test_gpu_kpconv.py: 1e-4 max-norm relative on fp32 features, exact on integers.
 """
@@ -93,7 +93,7 @@ def test_calibrate_neighbors_matches_oracle_counts(cuda):
 
 
 def test_config3_full_size_deformable(cuda, monkeypatch):
-    """BASELINE.json configs[3]: one 120k-point KITTI-shaped scan through the deformable architecture. Too large for
+    """BASELINE.json configs[2]: one 120k-point KITTI-shaped scan through the deformable architecture. Too large for
     the numpy restatement, so the check is the size-independent one: the tcgen05 3xTF32 path and the independent
     CUDA-core fp32 path (each pinned to the restatement at small sizes) agree to 1e-4 on every level, the pyramid
     is well-formed, and a second run is bit-identical (no atomics on float data)."""
@@ -101,7 +101,7 @@ def test_config3_full_size_deformable(cuda, monkeypatch):
     from d3feat_b200 import convolution_ops as co
     from d3feat_b200.encoder import KPFCNN
     # a 64-beam scan voxelised at the KITTI setting (0.3 m) keeps ~20k points; the 120k-point level 0 that
-    # configs[3] names is reached with a denser azimuth sampling and a 4 cm first voxel
+    # configs[2] names is reached with a denser azimuth sampling and a 4 cm first voxel
     cfg = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.04, first_features_dim=32)
     cloud = synth.lidar_scan(1, 120000, dl=0.04)
     L = np.array([cloud.shape[0]], np.int32)
