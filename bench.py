@@ -219,10 +219,11 @@ def main():
         l = L_pin.to(dev, non_blocking=True)
         out = enc(p, l, decoder=False)          # bbox computed on the device (one small D2H read)
         desc = out["F"][-1]
-        if world > 1:
-            desc, _ = all_gather_descriptors_padded(desc, out["inputs"]["lengths"][-1], gather_cap)
-        return desc.cpu()
+        if world > 1:      # the gathered matrix stays in HBM (that is where a matcher consumes it) ...
+            gathered[0], _ = all_gather_descriptors_padded(desc, out["inputs"]["lengths"][-1], gather_cap)
+        return desc.cpu()  # ... the host gets this rank's own descriptors
 
+    gathered = [None]      # the most recent all-gathered descriptor matrix (kept alive until the next step replaces it)
     flush_buf = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -261,8 +262,9 @@ def main():
         from d3feat_b200.encoder import BatchPipeline
 
         def post(inputs, desc):
-            if world > 1:      # the one exchange step: NCCL all-gather of the per-fragment descriptors (sync-free)
-                desc, _ = all_gather_descriptors_padded(desc, inputs["lengths"][-1], gather_cap)
+            if world > 1:      # the one exchange step: NCCL all-gather of the per-fragment descriptors (sync-free);
+                # the gathered matrix stays in HBM, the step returns this rank's own descriptors
+                gathered[0], _ = all_gather_descriptors_padded(desc, inputs["lengths"][-1], gather_cap)
             return desc
 
         pipe = BatchPipeline(enc, decoder=False, post=post)
@@ -377,6 +379,8 @@ def main():
                              d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
         line["config"]["l2"] = "256 MiB L2 flush at the start of every timed step"
+        line["config"]["e2e_output"] = ("every rank returns its own fragments' descriptors to its host; with N > 1 the "
+                                        "all-gathered matrix stays in HBM")
         line["config"]["pipeline"] = ("one batch at a time" if args.no_pipeline else
                                       "two streams: pyramid(i+1) || encoder(i) (encoder.BatchPipeline)")
         line["single_batch_latency_ms"] = seq_ms
