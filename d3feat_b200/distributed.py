@@ -33,7 +33,10 @@ def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group
         raise ValueError("all_gather_descriptors_padded: %d rows exceed the per-rank capacity %d" % (R, capacity))
     dev = local_desc.device
     world = _world(group)
-    meta = torch.cat([torch.tensor([R], dtype=torch.int64, device=dev), rows_per_fragment.to(torch.int64)])
+    # R enters the device as a fill-kernel argument: torch.tensor([R], device=...) would be a pageable host->device
+    # copy, which synchronises the stream first (the host would wait for the whole encoder queued before this call
+    # and the pyramid(i+1) || encoder(i) overlap would be lost on every rank)
+    meta = torch.cat([torch.full((1,), R, dtype=torch.int64, device=dev), rows_per_fragment.to(torch.int64)])
     padded = torch.zeros((capacity, D), dtype=local_desc.dtype, device=dev)
     padded[:R] = local_desc
     if world == 1:
