@@ -101,3 +101,33 @@ def test_detection_score_restatement_against_scalar_loop():
         local = np.log(1.0 + np.exp(xs[i] - rows.sum(axis=0) / num))
         depth = xs[i] / (1e-6 + xs[i].max())
         assert abs(got[i, 0] - (local * depth).max()) < 1e-12
+
+
+def test_pyramid_buffers_and_spec_on_cpu():
+    """PyramidBuffers (the pre-allocated ring slots of BatchPipeline) and the level radii for the KITTI session
+    (results_kitti/Log_11011605/parameters.txt:30: first_subsampling_dl = 0.3 -> conv radius 0.75, doubling per level)."""
+    import torch
+    from d3feat_b200 import pyramid as pyr, synth
+    cfg = synth.Config(first_subsampling_dl=0.3)
+    spec, levels = pyr.make_spec(cfg, [40, 41, 42, 43, 44])
+    assert spec.n_levels == 5
+    assert [round(float(spec.conv_radius[l]), 4) for l in range(5)] == [0.75, 1.5, 3.0, 6.0, 12.0]
+    assert [round(float(spec.sub_dl[l]), 4) for l in range(4)] == [0.6, 1.2, 2.4, 4.8] and spec.sub_dl[4] < 0
+    assert [round(float(spec.up_radius[l]), 4) for l in range(4)] == [1.5, 3.0, 6.0, 12.0]
+    assert [int(spec.limit[l]) for l in range(5)] == [40, 41, 42, 43, 44]
+    buf = pyr.PyramidBuffers(cfg, [40, 41, 42, 43, 44], capacity=1000, n_clouds=2, device=torch.device("cpu"))
+    assert buf.pts[0] is None and buf.pts[1].shape == (1000, 3) and buf.len[3].shape == (2,)
+    assert [b.shape[1] for b in buf.nb] == [40, 41, 42, 43, 44]
+    assert buf.pool[4] is None and buf.up[4] is None and buf.pool[0].shape == (1000, 40)
+    assert buf.fits(1000, 2, [40, 41, 42, 43, 44]) and not buf.fits(1001, 2, [40, 41, 42, 43, 44])
+    assert not buf.fits(10, 3, [40, 41, 42, 43, 44]) and not buf.fits(10, 2, [40] * 5)
+    w1 = buf.workspace(1000)
+    assert buf.workspace(900) is w1 and buf.workspace(5000).numel() >= 5000
+    # deformable blocks: the reference widens the CONV radius only when a deformable block precedes the last block of
+    # the level (`layer_blocks[:-1]`, datasets/common.py:1340); in this architecture that never happens, so only the
+    # pooling / upsampling radii of the deformable strided block grow by density_parameter / (KP_extent * 2.5)
+    cfgd = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.3)
+    specd, _ = pyr.make_spec(cfgd, [40] * 5)
+    assert [round(float(specd.conv_radius[l]), 3) for l in range(5)] == [0.75, 1.5, 3.0, 6.0, 12.0]
+    assert [round(float(specd.pool_radius[l]), 3) for l in range(4)] == [0.75, 1.5, 3.0, 12.0]
+    assert round(float(specd.up_radius[3]), 3) == 24.0
