@@ -181,9 +181,14 @@ def _kernel_points(K_radius, num_kpoints, device, fixed):
     name = V.scoped("kernel_points")
     if store is not None and name in store:
         return store.get(name)
-    # no checkpoint: seeded stand-in for kernels/kernel_points.py:184-280 (random rotation + 1 % noise)
+    if store is not None and len(store) > 0:
+        # a checkpoint is active but lacks this KPConv's saved disposition: never synthesise silently
+        raise KeyError("kernel points '%s' missing from the active ParamStore" % name)
+    # no checkpoint at all: seeded stand-in for kernels/kernel_points.py:184-280 (random rotation + 1 % noise). The
+    # seed is a stable hash of the variable name, so every process and every rank draws the same points.
+    import zlib
     from .synth import kernel_points
-    seed = abs(hash(name)) % (2 ** 31)
+    seed = zlib.crc32(name.encode("utf-8")) & 0x7FFFFFFF
     return torch.from_numpy(kernel_points(np.random.default_rng(seed), K_radius, num_kpoints)).to(device)
 
 

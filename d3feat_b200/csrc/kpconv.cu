@@ -252,13 +252,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 }
 
 template <int CPL, int QPW, bool DEFORM>
-#ifndef D3F_S1_MINB
-#define D3F_S1_MINB 6
-#endif
-#ifndef D3F_S1_UNROLL
-#define D3F_S1_UNROLL 4
-#endif
-__global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpconv_stage1_v2_kernel(Stage1Params p) {
+__global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : 6) kpconv_stage1_v2_kernel(Stage1Params p) {
   constexpr int K = 15, KP = 16;
   constexpr int LPQ = 32 / QPW;  // lanes (= neighbour slots per pass) per query
   static_assert(CPL == 2 || CPL == 4, "channels per lane");
@@ -321,10 +315,6 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
         w[k] = wk;
       }
       w[K] = 0.f;
-#ifdef D3F_S1_SKIP_A
-#pragma unroll
-      for (int k = 0; k < K; ++k) w[k] = rx * 1e-9f + 0.5f;
-#endif
       if (p.closest) {
 #pragma unroll
         for (int k = 0; k < K; ++k) w[k] = (k == kmin) ? w[k] : 0.f;
@@ -343,10 +333,7 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
 
       // ---- phase B: both half-warps walk their kept neighbours in lockstep, kUnroll per step: all row loads
       //      of a step are issued before the first FMA consumes one (memory-level parallelism) -------------
-      constexpr int kUnroll = CPL == 4 ? 2 : D3F_S1_UNROLL;
-#ifdef D3F_S1_SKIP_B
-      cnt = 0;
-#endif
+      constexpr int kUnroll = CPL == 4 ? 2 : 4;
       for (int it = 0; it < cnt; it += kUnroll) {
         int hh[kUnroll];
         float f[kUnroll][CPL];
@@ -357,10 +344,6 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
           m &= m - 1;
           const int idh = __shfl_sync(0xffffffffu, id, (int)gshift + hh[u]);
           const float* fp = p.feat + (size_t)idh * p.Cin + c;
-#ifdef D3F_S1_NO_LOAD
-          for (int v = 0; v < CPL; ++v) f[u][v] = act ? qx + (float)(idh + v) : 0.f;
-          (void)fp;
-#else
           if (CPL == 4) {
             float4 t = act ? __ldg(reinterpret_cast<const float4*>(fp)) : make_float4(0.f, 0.f, 0.f, 0.f);
             f[u][0] = t.x; f[u][1] = t.y; f[u][2 % CPL] = t.z; f[u][3 % CPL] = t.w;
@@ -368,7 +351,6 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
             float2 t = act ? __ldg(reinterpret_cast<const float2*>(fp)) : make_float2(0.f, 0.f);
             f[u][0] = t.x; f[u][1] = t.y;
           }
-#endif
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -381,28 +363,19 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
             wpair[2 * kq] = make_float2(t.x, t.y);
             wpair[2 * kq + 1] = make_float2(t.z, t.w);
           }
-#ifdef D3F_S1_NO_FMA
-#pragma unroll
-          for (int v = 0; v < CPL; ++v) acc[0][v].x += f[u][v] * wpair[v % (KP / 2)].x;
-#else
 #pragma unroll
           for (int v = 0; v < CPL; ++v) {
             const float2 fd = make_float2(f[u][v], f[u][v]);
 #pragma unroll
             for (int j = 0; j < KP / 2; ++j) acc[j][v] = ffma2(wpair[j], fd, acc[j][v]);
           }
-#endif
         }
       }
       __syncwarp();
     }
 
     // ---- write wf[n, k, c .. c+CPL) (optionally modulated, :489-490) ------------------------------------
-#ifdef D3F_S1_SKIP_STORE
-    if (qvalid && acc[0][0].x == 123.456f) {
-#else
     if (qvalid) {
-#endif
       float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
@@ -416,189 +389,6 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : D3F_S1_MINB) kpc
     }
   }
   if (p.inv_nn != nullptr && qvalid && sl == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Stage 1, staged version: the gather is the latency problem (ncu: long-scoreboard stalls at every row load,
-// profiles/r1_notes.md), so a warp first issues ALL row gathers of its query group as asynchronous 16-byte copies
-// into shared memory (cp.async, zero-fill for shadow / dropped neighbours), evaluates the kernel-point correlation
-// weights while they are in flight, and then runs the FFMA2 loop entirely out of shared memory.
-//   per warp: feature tile kHT x 512 B (kHT neighbour slots x QPW queries x LPQ lanes x 16 B) + weight tile.
-constexpr int kHT = 40;                                   // neighbour slots staged per pass over H
-constexpr int kS3FeatFloats = kHT * 128;                  // 512 B per slot row
-constexpr int kS3WarpFloats = kS3FeatFloats + 32 * kWStride + 4 * kKMax * 3;
-constexpr int kS3SmemBytes = kS1Warps * kS3WarpFloats * 4;
-
-__device__ __forceinline__ void cp_async16_zfill(float* dst_smem, const float* src, bool valid) {
-  unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-
-template <int CPL, int QPW, bool DEFORM>
-__global__ void __launch_bounds__(kS1Warps * 32, 2) kpconv_stage1_v3_kernel(Stage1Params p) {
-  constexpr int K = 15, KP = 16;
-  constexpr int LPQ = 32 / QPW;
-  constexpr int NJ = (kHT + LPQ - 1) / LPQ;   // slot groups per staged pass
-  static_assert(CPL == 4, "one 16-byte copy per lane and slot");
-  extern __shared__ __align__(16) float s3_smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* ftile = s3_smem + warp * kS3WarpFloats;
-  float* wts = ftile + kS3FeatFloats;
-  float* kp_s = wts + 32 * kWStride;           // [QPW][KP*3]
-  const int sub = lane / LPQ, sl = lane % LPQ;
-  const int nfirst = p.n0 + (blockIdx.x * kS1Warps + warp) * QPW;
-  if (nfirst >= p.n1) return;  // warp-uniform
-  const int n = nfirst + sub;
-  const bool qvalid = n < p.n1;
-  const int nslot = qvalid ? n : nfirst;
-  const int nq = p.order ? p.order[nslot] : nslot;
-
-  for (int t = sl; t < KP * 3; t += LPQ) {
-    float v = t < K * 3 ? p.Kp[t] : 0.f;
-    if (DEFORM && t < K * 3) v += p.offsets[(size_t)nq * K * 3 + t];
-    kp_s[sub * KP * 3 + t] = v;
-  }
-  const float qx = p.q[3 * (size_t)nq], qy = p.q[3 * (size_t)nq + 1], qz = p.q[3 * (size_t)nq + 2];
-  const int* row = p.idx + (size_t)nq * p.H;
-  const float ext2 = p.extent * p.extent;
-  const unsigned gshift = (unsigned)(sub * LPQ);
-  const unsigned gmask = LPQ == 32 ? 0xffffffffu : ((1u << LPQ) - 1u);
-  float* wq = wts + sub * LPQ * kWStride;
-  const float* kq = kp_s + sub * KP * 3;
-  __syncwarp();
-
-  int nn_count = 0;
-  constexpr int c_step = LPQ * CPL;
-  for (int c0 = 0; c0 < p.Cin; c0 += c_step) {
-    float2 acc[KP / 2][CPL];
-#pragma unroll
-    for (int j = 0; j < KP / 2; ++j)
-#pragma unroll
-      for (int v = 0; v < CPL; ++v) acc[j][v] = make_float2(0.f, 0.f);
-    const int c = c0 + sl * CPL;
-
-    for (int ht0 = 0; ht0 < p.H; ht0 += kHT) {
-      // ---- phase 0: neighbour ids of this lane's slots, support points, and ALL row gathers in flight --------
-      int id[NJ];
-      float4 sp[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const int hs = j * LPQ + sl;          // slot inside the staged pass
-        const int h = ht0 + hs;
-        int v = (hs < kHT && h < p.H) ? row[h] : p.Ns;
-        if (v < 0 || v > p.Ns) v = p.Ns;
-        id[j] = v;
-      }
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) sp[j] = __ldg(&p.s4[id[j]]);
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-#pragma unroll
-        for (int t = 0; t < LPQ; ++t) {
-          const int hs = j * LPQ + t;
-          if (hs < kHT) {
-            const int idh = __shfl_sync(0xffffffffu, id[j], (int)gshift + t);
-            const bool ok = idh < p.Ns && qvalid;
-            cp_async16_zfill(ftile + hs * 128 + lane * 4, p.feat + (size_t)(ok ? idh : 0) * p.Cin + c, ok);
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        // ---- phase A: correlation weights of slot group j (overlaps the copies for j == 0) --------------------
-        const bool real = id[j] < p.Ns;
-        const float rx = sp[j].x - qx, ry = sp[j].y - qy, rz = sp[j].z - qz;
-        float w[KP];
-        float dmin = 3.0e38f;
-        int kmin = 0;
-        bool in_range = false;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          float dx = rx - kq[3 * k], dy = ry - kq[3 * k + 1], dz = rz - kq[3 * k + 2];
-          float d2 = dx * dx + dy * dy + dz * dz;
-          if (d2 < dmin) { dmin = d2; kmin = k; }
-          in_range = in_range || (d2 < ext2);
-          float wk;
-          if (p.influence == D3F_INFLUENCE_LINEAR) wk = fmaxf(1.f - sqrt_approx(d2 + 1e-10f) * p.inv_scale, 0.f);
-          else if (p.influence == D3F_INFLUENCE_GAUSSIAN) wk = __expf(-d2 * p.gauss_inv);
-          else wk = DEFORM ? (d2 < ext2 ? 1.f : 0.f) : 1.f;
-          w[k] = wk;
-        }
-        w[K] = 0.f;
-        if (p.closest) {
-#pragma unroll
-          for (int k = 0; k < K; ++k) w[k] = (k == kmin) ? w[k] : 0.f;
-        }
-        const bool keep = real && qvalid && (!DEFORM || in_range);
-#pragma unroll
-        for (int kk = 0; kk < KP / 4; ++kk)
-          *reinterpret_cast<float4*>(&wq[sl * kWStride + 4 * kk]) =
-              keep ? make_float4(w[4 * kk], w[4 * kk + 1], w[4 * kk + 2], w[4 * kk + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 == 0 && p.count_nn) nn_count += __popc((__ballot_sync(0xffffffffu, sp[j].w > 0.f) >> gshift) & gmask);
-        unsigned m = (__ballot_sync(0xffffffffu, keep) >> gshift) & gmask;
-        int cnt = __popc(m);
-        if (QPW >= 2) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
-        if (QPW >= 4) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 8));
-        if (j == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-
-        // ---- phase B: FFMA2 over the kept slots, features and weights both from shared memory ----------------
-        for (int it = 0; it < cnt; ++it) {
-          const bool act = m != 0;
-          const int t = act ? __ffs(m) - 1 : 0;
-          m &= m - 1;
-          float4 f = *reinterpret_cast<const float4*>(ftile + (j * LPQ + t) * 128 + lane * 4);
-          if (!act) f = make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4* wp = reinterpret_cast<const float4*>(&wq[t * kWStride]);
-          float2 wpair[KP / 2];
-#pragma unroll
-          for (int kk = 0; kk < KP / 4; ++kk) {
-            float4 tw = wp[kk];
-            wpair[2 * kk] = make_float2(tw.x, tw.y);
-            wpair[2 * kk + 1] = make_float2(tw.z, tw.w);
-          }
-          const float fv[4] = {f.x, f.y, f.z, f.w};
-#pragma unroll
-          for (int v = 0; v < CPL; ++v) {
-            const float2 fd = make_float2(fv[v], fv[v]);
-#pragma unroll
-            for (int jj = 0; jj < KP / 2; ++jj) acc[jj][v] = ffma2(wpair[jj], fd, acc[jj][v]);
-          }
-        }
-        __syncwarp();
-      }
-    }
-
-    if (qvalid) {
-      float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float mod = (DEFORM && p.modulations) ? p.modulations[(size_t)nq * K + k] : 1.f;
-        float o[CPL];
-#pragma unroll
-        for (int v = 0; v < CPL; ++v) o[v] = ((k & 1) ? acc[k / 2][v].y : acc[k / 2][v].x) * mod;
-        *reinterpret_cast<float4*>(dst + (size_t)k * p.Cin) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-    }
-  }
-  if (p.inv_nn != nullptr && qvalid && sl == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
-}
-
-template <int QPW, bool DEFORM>
-static int launch_stage1_v3(const Stage1Params& p, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    D3F_CUDA(cudaFuncSetAttribute(kpconv_stage1_v3_kernel<4, QPW, DEFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kS3SmemBytes));
-    configured = true;
-  }
-  int nq = p.n1 - p.n0;
-  kpconv_stage1_v3_kernel<4, QPW, DEFORM><<<ceil_div(nq, kS1Warps * QPW), kS1Warps * 32, kS3SmemBytes, stream>>>(p);
-  D3F_LAUNCH_CHECK("kpconv_stage1_v3_kernel");
-  return D3F_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -755,14 +545,91 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1
   if (p.inv_nn != nullptr && lane == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
 }
 
-template <int K, bool DEFORM>
-static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------------
+// Stage 1 for any number of kernel points (config.num_kernel_points, utils/config.py; D3Feat ships K = 15, for which the
+// specialised kernels above exist). One warp per query; the correlation weights of a 32-neighbour chunk live in shared
+// memory [k][neighbour], wf[n,k,:] is accumulated chunk by chunk in global memory (the chunk's rows are re-read per
+// kernel point out of L1). Correctness path, not a tuned one.
+constexpr int kAnyKMax = 64;
+
+template <bool DEFORM>
+__global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_anyk_kernel(Stage1Params p, int K) {
+  extern __shared__ float anyk_smem[];   // per warp: wts[K][32], kp[K][3]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* wts = anyk_smem + (size_t)warp * (K * 32 + K * 3);
+  float* kp_s = wts + K * 32;
+  const int n = p.n0 + blockIdx.x * kS1Warps + warp;
+  if (n >= p.n1) return;  // warp-uniform
+  const int qid = p.order ? p.order[n] : n;
+  for (int t = lane; t < K * 3; t += 32) {
+    float v = p.Kp[t];
+    if (DEFORM) v += p.offsets[(size_t)qid * K * 3 + t];
+    kp_s[t] = v;
+  }
+  const float qx = p.q[3 * (size_t)qid], qy = p.q[3 * (size_t)qid + 1], qz = p.q[3 * (size_t)qid + 2];
+  const int* row = p.idx + (size_t)qid * p.H;
+  const float ext2 = p.extent * p.extent;
+  float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin;
+  __syncwarp();
+  int nn_count = 0;
+  for (int h0 = 0; h0 < p.H || h0 == 0; h0 += 32) {
+    const int h = h0 + lane;
+    int id = (h < p.H) ? row[h] : p.Ns;
+    if (id < 0 || id > p.Ns) id = p.Ns;
+    const bool real = id < p.Ns;
+    const float4 sp = __ldg(&p.s4[id]);
+    const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
+    float dmin = 3.0e38f;
+    int kmin = 0;
+    bool in_range = false;
+    for (int k = 0; k < K; ++k) {
+      float dx = rx - kp_s[3 * k], dy = ry - kp_s[3 * k + 1], dz = rz - kp_s[3 * k + 2];
+      float d2 = dx * dx + dy * dy + dz * dz;
+      if (d2 < dmin) { dmin = d2; kmin = k; }
+      in_range = in_range || (d2 < ext2);
+      float wk;
+      if (p.influence == D3F_INFLUENCE_LINEAR) wk = fmaxf(1.f - sqrtf(d2 + 1e-10f) * p.inv_scale, 0.f);
+      else if (p.influence == D3F_INFLUENCE_GAUSSIAN) wk = expf(-d2 * p.gauss_inv);
+      else wk = DEFORM ? (d2 < ext2 ? 1.f : 0.f) : 1.f;
+      wts[k * 32 + lane] = wk;
+    }
+    const bool keep = real && (!DEFORM || in_range);
+    for (int k = 0; k < K; ++k) {
+      float wk = wts[k * 32 + lane];
+      if (p.closest && k != kmin) wk = 0.f;
+      if (!keep) wk = 0.f;
+      if (DEFORM && p.modulations) wk *= p.modulations[(size_t)qid * K + k];   // wf_k * mod_k (:489-490)
+      wts[k * 32 + lane] = wk;
+    }
+    if (p.count_nn) nn_count += __popc(__ballot_sync(0xffffffffu, sp.w > 0.f));
+    const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    for (int c0 = 0; c0 < p.Cin; c0 += 32) {   // every lane runs every iteration (full-mask shuffles inside)
+      const int c = c0 + lane;
+      const bool c_ok = c < p.Cin;
+      for (int k = 0; k < K; ++k) {
+        float acc = (h0 == 0 || !c_ok) ? 0.f : dst[(size_t)k * p.Cin + c];
+        unsigned m = keep_mask;
+        while (m) {
+          const int j = __ffs(m) - 1;
+          m &= m - 1;
+          const int idj = __shfl_sync(0xffffffffu, id, j);
+          if (c_ok) acc = fmaf(wts[k * 32 + j], p.feat[(size_t)idj * p.Cin + c], acc);
+        }
+        if (c_ok) dst[(size_t)k * p.Cin + c] = acc;
+      }
+    }
+    __syncwarp();
+  }
+  if (p.inv_nn != nullptr && lane == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(nn_count, 1);
+}
+
+template <bool DEFORM>
+static int launch_stage1(int K, const Stage1Params& p, cudaStream_t stream) {
   int nq = p.n1 - p.n0;
   bool al16 = (reinterpret_cast<uintptr_t>(p.feat) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.wf) & 15) == 0;
-#ifndef D3F_NO_MMA_STAGE1
   if (K == 15 && al16 && (p.Cin == 32 || p.Cin == 64 || p.Cin % 128 == 0)) {
     const int blocks = ceil_div(nq, kS1Warps);
-#if 1
     const bool fast = p.influence == D3F_INFLUENCE_LINEAR && !p.closest;
     if (fast) {
       if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM, true><<<blocks, kS1Warps * 32, 0, stream>>>(p);
@@ -773,32 +640,22 @@ static int launch_stage1(const Stage1Params& p, cudaStream_t stream) {
       else if (p.Cin == 64) kpconv_stage1_mma_kernel<8, DEFORM, false><<<blocks, kS1Warps * 32, 0, stream>>>(p);
       else kpconv_stage1_mma_kernel<16, DEFORM, false><<<blocks, kS1Warps * 32, 0, stream>>>(p);
     }
-#endif
     D3F_LAUNCH_CHECK("kpconv_stage1_mma_kernel");
     return D3F_OK;
   }
-#endif
-#ifdef D3F_STAGED   // measured slower than the direct-gather kernel on B200 (profiles/r1_notes.md); kept for experiments
-  if (K == 15 && al16 && p.Cin % 128 == 0) return launch_stage1_v3<1, DEFORM>(p, stream);
-  if (K == 15 && al16 && p.Cin == 64) return launch_stage1_v3<2, DEFORM>(p, stream);
-  if (K == 15 && al16 && p.Cin == 32) return launch_stage1_v3<4, DEFORM>(p, stream);
-#endif
   // (channels per lane, queries per warp): every broadcast weight read should feed as much math as possible
   if (K == 15 && al16 && p.Cin % 128 == 0) {
     kpconv_stage1_v2_kernel<4, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
-#ifdef D3F_WIDE_LANES   // (4 ch/lane, 2-4 queries/warp): measured 5-8 % slower than the mappings below on B200
-  } else if (K == 15 && al16 && p.Cin == 64) {
-    kpconv_stage1_v2_kernel<4, 2, DEFORM><<<ceil_div(nq, kS1Warps * 2), kS1Warps * 32, 0, stream>>>(p);
-  } else if (K == 15 && al16 && p.Cin == 32) {
-    kpconv_stage1_v2_kernel<4, 4, DEFORM><<<ceil_div(nq, kS1Warps * 4), kS1Warps * 32, 0, stream>>>(p);
-#endif
   } else if (K == 15 && al16 && p.Cin % 64 == 0) {
     kpconv_stage1_v2_kernel<2, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
   } else if (K == 15 && al16 && p.Cin % 32 == 0) {
     kpconv_stage1_v2_kernel<2, 2, DEFORM><<<ceil_div(nq, kS1Warps * 2), kS1Warps * 32, 0, stream>>>(p);
+  } else if (K == 15) {
+    // generic K = 15 path (odd widths)
+    kpconv_stage1_kernel<15, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
   } else {
-    // generic path (first layer Cin = 1, odd widths)
-    kpconv_stage1_kernel<K, 1, DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, 0, stream>>>(p);
+    const size_t smem = (size_t)kS1Warps * (K * 32 + K * 3) * sizeof(float);
+    kpconv_stage1_anyk_kernel<DEFORM><<<ceil_div(nq, kS1Warps), kS1Warps * 32, smem, stream>>>(p, K);
   }
   D3F_LAUNCH_CHECK("kpconv_stage1_kernel");
   return D3F_OK;
@@ -889,26 +746,41 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
   }
 }
 
-// Auxiliary stream + events for the chunk pipeline. Thread-local (one set per host thread), created lazily for the
-// current device: the library stays re-entrant across host threads, nothing is shared between them.
+// Auxiliary stream + events for the chunk pipeline: one set per (host thread, device), created lazily and destroyed
+// with the host thread. Nothing is shared between host threads, so the library stays re-entrant.
 struct AuxStream {
-  int device = -1;
   cudaStream_t stream = nullptr;
   cudaEvent_t s1_done[2] = {nullptr, nullptr};
   cudaEvent_t gemm_done[2] = {nullptr, nullptr};
 };
+constexpr int kMaxDevices = 32;
+struct AuxStreams {
+  AuxStream dev[kMaxDevices];
+  ~AuxStreams() {   // errors ignored: at process exit the context may already be gone
+    for (int d = 0; d < kMaxDevices; ++d) {
+      if (dev[d].stream == nullptr) continue;
+      int cur = 0;
+      if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(d) != cudaSuccess) continue;
+      for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(dev[d].s1_done[i]);
+        cudaEventDestroy(dev[d].gemm_done[i]);
+      }
+      cudaStreamDestroy(dev[d].stream);
+      cudaSetDevice(cur);
+    }
+  }
+};
 static AuxStream* aux_stream() {
-  static thread_local AuxStream a;
+  static thread_local AuxStreams all;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  if (a.stream != nullptr && a.device == dev) return &a;
-  if (a.stream != nullptr) return nullptr;   // a second device from the same thread: run un-overlapped
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  AuxStream& a = all.dev[dev];
+  if (a.stream != nullptr) return &a;
   if (cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking) != cudaSuccess) { a.stream = nullptr; return nullptr; }
   for (int i = 0; i < 2; ++i) {
     cudaEventCreateWithFlags(&a.s1_done[i], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&a.gemm_done[i], cudaEventDisableTiming);
   }
-  a.device = dev;
   return &a;
 }
 
@@ -943,7 +815,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
                         float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   D3F_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 0 && Cin >= 1 && Cout >= 1, D3F_ERR_INVALID,
               "kpconv: bad shape Nq=%d Ns=%d H=%d Cin=%d Cout=%d", Nq, Ns, H, Cin, Cout);
-  D3F_REQUIRE(K == 15, D3F_ERR_INVALID, "kpconv: num_kernel_points=%d not instantiated (built for K=15)", K);
+  D3F_REQUIRE(K >= 1 && K <= kAnyKMax, D3F_ERR_INVALID, "kpconv: num_kernel_points=%d outside [1, %d]", K, kAnyKMax);
   D3F_REQUIRE(influence >= 0 && influence <= 2, D3F_ERR_INVALID,
               "Unknown influence function type (config.KP_influence)");
   D3F_REQUIRE(mode == D3F_MODE_SUM || mode == D3F_MODE_CLOSEST, D3F_ERR_INVALID,
@@ -964,7 +836,8 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   float* split_ws = split_floats ? cv.take<float>(split_floats) : nullptr;
   const bool norm = normalize != 0 && !deform;
   {
-    int pmode = (Cin == 1 && !deform) ? 2 : (norm ? 1 : 0);
+    const bool first_layer = Cin == 1 && !deform && K == 15;
+    int pmode = first_layer ? 2 : (norm ? 1 : 0);
     const float shadow = deform ? 1000.f : 1e6f;
     const bool vec = pmode == 1 && Cin % 4 == 0 && Cin >= 32 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
     if (vec && Cin < 64)
@@ -977,7 +850,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
       prep_supports_kernel<<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, pmode, shadow, s4);
     D3F_LAUNCH_CHECK("prep_supports_kernel");
   }
-  if (Cin == 1 && !deform) {
+  if (Cin == 1 && !deform && K == 15) {
     Cin1Params c1;
     c1.q = q; c1.s4 = s4; c1.idx = idx; c1.Kp = Kp; c1.W = W;
     c1.Nq = Nq; c1.Ns = Ns; c1.H = H; c1.Cout = Cout;
@@ -1022,7 +895,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     p.n0 = n0;
     p.n1 = min(Nq, n0 + chunk);
     if (aux && ci >= 2) D3F_CUDA(cudaStreamWaitEvent(stream, aux->gemm_done[b], 0));   // buffer b free again
-    int rc = deform ? launch_stage1<15, true>(p, stream) : launch_stage1<15, false>(p, stream);
+    int rc = deform ? launch_stage1<true>(K, p, stream) : launch_stage1<false>(K, p, stream);
     if (rc) return rc;
     cudaStream_t gs = stream;
     if (aux) {

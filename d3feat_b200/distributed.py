@@ -19,24 +19,33 @@ def _world(group):
     return dist.get_world_size(group)
 
 
-def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group=None):
+def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group=None, max_fragments=None):
     """Sync-free gather used on the hot path.
 
     local_desc: float32[R, D] stacked descriptors of this rank's fragments (R is the tensor's shape, host-known);
     rows_per_fragment: int tensor [F] ON THE DEVICE (the last pyramid level's stack lengths) -- it is never read
-    on the host here; capacity: rows reserved per rank (>= R on every rank).
-    Returns (gathered [world, capacity, D], meta [world, 1 + F] int64 = [R, rows per fragment...]), both on the
-    device; no host synchronisation, two collectives (one of them a few bytes).
+    on the host here; capacity: rows reserved per rank (>= R on every rank); max_fragments: fragments reserved per
+    rank (>= F on every rank; default F, which then must be the same on all ranks -- with round-robin sharding that
+    only holds when n_fragments % world == 0).
+    Returns (gathered [world, capacity, D], meta [world, 2 + max_fragments] int64 = [R, F, rows per fragment...,
+    zero padding]), both on the device; no host synchronisation, two collectives (one of them a few bytes).
     """
     R, D = local_desc.shape
     if R > capacity:
         raise ValueError("all_gather_descriptors_padded: %d rows exceed the per-rank capacity %d" % (R, capacity))
+    F = int(rows_per_fragment.shape[0])
+    Fmax = F if max_fragments is None else int(max_fragments)
+    if F > Fmax:
+        raise ValueError("all_gather_descriptors_padded: %d fragments exceed max_fragments %d" % (F, Fmax))
     dev = local_desc.device
     world = _world(group)
-    # R enters the device as a fill-kernel argument: torch.tensor([R], device=...) would be a pageable host->device
+    # R and F enter the device as fill-kernel arguments: torch.tensor([R], device=...) would be a pageable host->device
     # copy, which synchronises the stream first (the host would wait for the whole encoder queued before this call
     # and the pyramid(i+1) || encoder(i) overlap would be lost on every rank)
-    meta = torch.cat([torch.full((1,), R, dtype=torch.int64, device=dev), rows_per_fragment.to(torch.int64)])
+    meta = torch.zeros((2 + Fmax,), dtype=torch.int64, device=dev)
+    meta[0:1].fill_(R)
+    meta[1:2].fill_(F)
+    meta[2:2 + F] = rows_per_fragment.to(torch.int64)
     padded = torch.zeros((capacity, D), dtype=local_desc.dtype, device=dev)
     padded[:R] = local_desc
     if world == 1:
@@ -54,22 +63,23 @@ def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group
 
 def unpack_gathered(gathered, metas):
     """Host-side compaction of the padded gather: (desc_all [sum R, D], rows_all list[int], owner list[int]);
-    rank 0's fragments first, then rank 1's, ... (each rank's own order preserved). Synchronises."""
+    rank 0's fragments first, then rank 1's, ... (each rank's own order preserved; fragments with zero rows keep
+    their slot). Synchronises."""
     m = metas.cpu()
     world = m.shape[0]
     rows = [int(m[r, 0]) for r in range(world)]
     desc_all = torch.cat([gathered[r, :rows[r]] for r in range(world)], 0)
     rows_all, owner = [], []
     for r in range(world):
-        per = [int(x) for x in m[r, 1:] if int(x) > 0]   # zero entries pad ranks that own fewer fragments
-        rows_all += per
-        owner += [r] * len(per)
+        nf = int(m[r, 1])                                 # explicit fragment count: zero-row fragments are not padding
+        rows_all += [int(x) for x in m[r, 2:2 + nf]]
+        owner += [r] * nf
     return desc_all, rows_all, owner
 
 
 def all_gather_descriptors(local_desc, local_rows_per_fragment, group=None):
     """Convenience form with exact shapes (reads sizes on the host): returns
-    (desc_all [R_total, D], rows_all list[int], owner list[int])."""
+    (desc_all [R_total, D], rows_all list[int], owner list[int]). Ranks may own different numbers of fragments."""
     if _world(group) == 1:
         return local_desc, list(local_rows_per_fragment), [0] * len(local_rows_per_fragment)
     dev = local_desc.device
@@ -80,15 +90,6 @@ def all_gather_descriptors(local_desc, local_rows_per_fragment, group=None):
     dist.all_gather(all_sizes, sizes, group=group)
     cap = max(int(s[0]) for s in all_sizes)
     fmax = max(int(s[1]) for s in all_sizes)
-    rows_t = torch.zeros((max(fmax, 1),), dtype=torch.int64, device=dev)
-    if n_local:
-        rows_t[:n_local] = torch.tensor(list(local_rows_per_fragment), dtype=torch.int64, device=dev)
-    gathered, metas = all_gather_descriptors_padded(local_desc, rows_t, max(cap, 1), group)
-    desc_all, _, _ = unpack_gathered(gathered, metas)
-    m = metas.cpu()
-    rows_all, owner = [], []
-    for r in range(world):
-        nf = int(all_sizes[r][1])
-        rows_all += [int(x) for x in m[r, 1:1 + nf]]
-        owner += [r] * nf
-    return desc_all, rows_all, owner
+    rows_t = torch.tensor(list(local_rows_per_fragment), dtype=torch.int64, device=dev).reshape(-1)
+    gathered, metas = all_gather_descriptors_padded(local_desc, rows_t, max(cap, 1), group, max_fragments=max(fmax, 1))
+    return unpack_gathered(gathered, metas)

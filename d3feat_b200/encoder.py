@@ -103,11 +103,15 @@ class BatchPipeline:
             self.slots[k] = buf
         return k, buf
 
-    def _build(self, points, lengths, bbox):
+    def _build(self, points, lengths, bbox, inputs_ready):
         k, buf = self._slot(int(points.shape[0]), int(lengths.shape[0]))
+        self.s_pyr.wait_event(inputs_ready)   # caller-produced CUDA inputs are complete before the pyramid reads them
         with torch.cuda.stream(self.s_pyr):
             inputs = self.enc.build_inputs(points, lengths, bbox=bbox, buffers=buf)
             self.ready.record(self.s_pyr)
+        for t in (points, lengths):           # caller tensors are read on the pyramid stream
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(self.s_pyr)
         inputs["_slot"] = k
         for v in inputs.values():             # the pyramid's tensors are consumed on the encoder stream
             for t in (v if isinstance(v, (list, tuple)) else [v]):
@@ -115,13 +119,27 @@ class BatchPipeline:
                     t.record_stream(self.s_enc)
         return inputs
 
+    def _mark_inputs(self):
+        """Event on the caller's current stream: everything the caller enqueued so far (the next batch's CUDA inputs)."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.enc.device))
+        return ev
+
     def prime(self, points, lengths, bbox=None):
-        self.pending = self._build(points, lengths, bbox)
+        self.pending = self._build(points, lengths, bbox, self._mark_inputs())
 
     def step(self, next_points=None, next_lengths=None, next_bbox=None, pre=None):
         """Enqueue encoder(current batch) on the encoder stream, then build the pyramid of the next batch on the
-        pyramid stream (the host blocks only in that stream's size read-backs). Returns the current batch's result."""
+        pyramid stream (the host blocks only in that stream's size read-backs). Returns the current batch's result.
+
+        Stream contract: the result is produced on the private encoder stream; before returning, the CALLER's
+        current stream is made to wait for it (an event, no host sync) and the result's memory is tied to that
+        stream, so `res.cpu()` or a kernel launched on the caller's stream reads finished data."""
         inputs = self.pending
+        cur = torch.cuda.current_stream(self.enc.device)
+        # taken BEFORE `cur` is made to wait for this batch's encoder: the next pyramid then depends on the caller's
+        # inputs only, not on encoder(i) -- the pyramid(i+1) || encoder(i) overlap is preserved
+        inputs_ready = self._mark_inputs() if next_points is not None else None
         with torch.cuda.stream(self.s_enc):
             self.s_enc.wait_event(self.ready)
             if pre is not None:
@@ -133,8 +151,14 @@ class BatchPipeline:
             ev = torch.cuda.Event()
             ev.record(self.s_enc)
             self.done[inputs["_slot"]] = ev
+        cur.wait_event(ev)
+        for t in (res if isinstance(res, (list, tuple)) else [res]):
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(cur)
+        self.result_event = ev
         self.keep = [inputs, F]
-        self.pending = self._build(next_points, next_lengths, next_bbox) if next_points is not None else None
+        self.pending = (self._build(next_points, next_lengths, next_bbox, inputs_ready)
+                        if next_points is not None else None)
         return res
 
     def drain(self):

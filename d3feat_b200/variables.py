@@ -26,6 +26,9 @@ class ParamStore:
     def __contains__(self, name):
         return name in self.t
 
+    def __len__(self):
+        return len(self.t)
+
     def get(self, name):
         try:
             return self.t[name]

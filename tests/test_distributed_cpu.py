@@ -32,7 +32,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         frags = shard_fragments(5, rank, world)          # rank 0: 0,2,4   rank 1: 1,3
-        rows = [10 + 3 * f for f in frags]
+        rows = [0 if f == 3 else 10 + 3 * f for f in frags]   # fragment 3 is empty: keeps its slot
         desc = torch.cat([torch.full((r, 4), float(f)) + torch.arange(r)[:, None] / 100.0 for f, r in zip(frags, rows)], 0)
         all_desc, all_rows, owner = all_gather_descriptors(desc, rows)
         np.save(os.path.join(out_dir, "d%d.npy" % rank), all_desc.numpy())
@@ -50,7 +50,7 @@ def test_all_gather_descriptors_gloo_world2(tmp_path):
     assert np.array_equal(d0, d1)                       # every rank ends with the same gathered matrix
     rows = np.load(tmp_path / "r0.npy").tolist()
     owner = np.load(tmp_path / "o0.npy").tolist()
-    assert rows == [10, 16, 22, 13, 19] and owner == [0, 0, 0, 1, 1]
+    assert rows == [10, 16, 22, 13, 0] and owner == [0, 0, 0, 1, 1]   # unequal counts per rank, zero-row fragment kept
     assert d0.shape == (sum(rows), 4)
     # fragment ids are encoded in the integer part: rank 0's fragments first, then rank 1's, padding removed
     frag_of_row = np.floor(d0[:, 0]).astype(int)
