@@ -3,12 +3,16 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
     python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle/_ref + restatement)
+    python bench.py --workload single30k|kitti120k|micro1m   # the other BASELINE configs (side lines, same JSON shape)
 
-A step = one pass of the hot path (4 grid subsamplings + 13 radius searches + 10 KPConv + 23 unary convs +
-BN/LeakyReLU/pools) over one batch of `--fragments` stacked synthetic 3DMatch-shaped fragments of `--points`
-points (BASELINE configs[1], stacked like configs[3]: 8 fragments per GPU). value = level-0 points / second,
-whole job. For N > 1 every rank runs its own fragments (weak scaling) and the step ends with the NCCL
-all-gather of the per-fragment descriptors.
+Default workload `batch8x30k`: a step = one pass of the hot path (4 grid subsamplings + 13 radius searches + 10 KPConv +
+23 unary convs + BN/LeakyReLU/pools) over one batch of 8 stacked synthetic 3DMatch-shaped fragments of 30 000 points
+per GPU (BASELINE configs[1] stacked as in configs[3]). value = level-0 points / second, whole job. For N > 1 every
+rank runs its own fragments (weak scaling) and the step ends with the NCCL all-gather of the per-fragment descriptors.
+
+Both arms print the SAME `config` (arm-specific notes live under `detail`). The reference arm runs exactly the
+workload it prints -- full-size fragments; when K + W full steps would not finish within a few minutes it runs fewer
+timed steps and says so (`steps_run`), it never shrinks the fragments.
 """
 import argparse
 import json
@@ -16,7 +20,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -25,7 +28,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-LIMITS = [40, 40, 40, 40, 40]      # "max 40 neighbors" (north_star); calibrated caps are 35-40 on real fragments
+WORKLOADS = ("batch8x30k", "single30k", "kitti120k", "micro1m")
+REF_ARM_BUDGET_S = 200.0          # the reference arm cuts STEPS (never points) to stay inside this
 
 
 def parse():
@@ -34,10 +38,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--fragments", type=int, default=8, help="fragments stacked per GPU per step")
-    ap.add_argument("--points", type=int, default=30000, help="level-0 points per fragment")
+    ap.add_argument("--workload", default="batch8x30k", choices=WORKLOADS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="one batch at a time on one stream")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     return ap.parse_args()
 
 
@@ -49,9 +53,59 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+# ----------------------------------------------------------------------------------------------------
+#  algorithmic bytes -- the figures `roofline.achieved` is computed from
+# ----------------------------------------------------------------------------------------------------
+
 def kpconv_algorithmic_bytes(Nq, H, K, Cin, Cout):
-    """SURVEY.md 8(d): bytes = Nq*H*(4 + 12 + 4*Cin) + 4*Nq*Cout + 4*K*Cin*Cout + 12*Nq."""
+    """bytes = Nq*H*(4 + 12 + 4*Cin) + 4*Nq*Cout + 4*K*Cin*Cout + 12*Nq."""
     return Nq * H * (4 + 12 + 4 * Cin) + 4 * Nq * Cout + 4 * K * Cin * Cout + 12 * Nq
+
+
+def unary_algorithmic_bytes(N, Cin, Cout, residual=False):
+    return 4 * N * (Cin + Cout + (Cout if residual else 0)) + 4 * Cin * Cout
+
+
+def neighbors_algorithmic_bytes(Nq, Ns, cols):
+    """12*(Nq + Ns) + 4*Nq*cols (the 27-cell candidate reads are cache traffic, not counted)."""
+    return 12 * (Nq + Ns) + 4 * Nq * cols
+
+
+def subsample_algorithmic_bytes(N, M):
+    """12*N in + 12*M out + 8*N keys."""
+    return 12 * N + 12 * M + 8 * N
+
+
+# ----------------------------------------------------------------------------------------------------
+#  workloads
+# ----------------------------------------------------------------------------------------------------
+
+def make_workload(name, rank):
+    """(config object, neighbour caps, list of level-0 clouds of this rank, JSON description)."""
+    from d3feat_b200 import synth
+    if name in ("batch8x30k", "single30k"):
+        nfrag = 8 if name == "batch8x30k" else 1
+        cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+        limits = [40, 40, 40, 40, 40]      # "max 40 neighbors" (north_star); calibrated caps are 35-40 on real fragments
+        clouds = [synth.room_fragment(rank * nfrag + i, 30000) for i in range(nfrag)]
+        desc = dict(workload="%d stacked 3DMatch-shaped synthetic fragment%s x 30000 pts per GPU, full 5-level KPFCNN "
+                             "encoder" % (nfrag, "s" if nfrag > 1 else ""),
+                    baseline_config="configs[1] stacked as in configs[3]" if nfrag > 1 else "configs[1]",
+                    fragments_per_gpu=nfrag, points_per_fragment=30000, levels=5, K=15, neighbor_cols=limits,
+                    first_subsampling_dl=0.03, params_seed=0)
+        return cfg, limits, clouds, desc, 0
+    if name == "kitti120k":
+        cfg = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.04, first_features_dim=32)
+        limits = [40, 40, 40, 60, 40]
+        clouds = [synth.lidar_scan(1 + rank, 120000, dl=0.04)]
+        desc = dict(workload="KITTI-shaped synthetic 64-beam scan, 120000 level-0 pts per GPU, 5-level encoder with "
+                             "deformable KPConv in the last three blocks",
+                    baseline_config="configs[2]", fragments_per_gpu=1, points_per_fragment=120000, levels=5, K=15,
+                    neighbor_cols=limits, first_subsampling_dl=0.04, params_seed=1,
+                    note="a 64-beam scan voxelised at the reference's 0.30 m keeps < 25k points; the 120k level-0 "
+                         "points configs[2] names are reached with a 4 cm first voxel")
+        return cfg, limits, clouds, desc, 1
+    raise ValueError(name)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -71,33 +125,68 @@ def cpu_one_fragment(cfg, params, pts, limits, use_ref):
     return F[-1]
 
 
-def cpu_reference_run(cfg, params, n_points, steps, warmup):
-    """Each step: T = min(nproc, 8) fragments in parallel threads (the reference's tf.data map runs
-    input_threads = 8 pyramids concurrently, training_3DMatch.py:35; ctypes and BLAS release the GIL)."""
+def cpu_reference_run(cfg, params, clouds, limits, steps, warmup, budget_s):
+    """Each step processes ALL `clouds` (the same fragments one GPU step processes), one fragment per host thread, with
+    every host core in use: T = min(nproc, fragments) worker threads (the reference's tf.data map runs its pyramids
+    concurrently the same way, datasets/common.py:600,744) and nproc // T BLAS threads inside each numpy call.
+    Returns (per-step seconds, info)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import native as on
-    from d3feat_b200 import synth
     use_ref = on.have_ref()
     if not use_ref:
         on.port()
     nproc = os.cpu_count() or 1
-    T = max(1, min(nproc, 8))
-    frags = [synth.room_fragment(100 + i, n_points) for i in range(T)]
+    T = max(1, min(nproc, len(clouds)))
+    blas = max(1, nproc // T)
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=blas)
+    except Exception:                      # threadpoolctl missing: BLAS keeps its default
+        limiter, blas = None, None
     times = []
+    t_start = time.perf_counter()
     with ThreadPoolExecutor(T) as ex:
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            list(ex.map(lambda p: cpu_one_fragment(cfg, params, p, LIMITS, use_ref), frags))
+            list(ex.map(lambda p: cpu_one_fragment(cfg, params, p, limits, use_ref), clouds))
             dt = time.perf_counter() - t0
             if it >= warmup:
                 times.append(dt)
-    ms = 1000.0 * float(np.mean(times))
-    value = T * n_points / (ms / 1000.0)
+            done_timed = len(times)
+            elapsed = time.perf_counter() - t_start
+            if done_timed >= 3 and elapsed + 1.5 * dt > budget_s:
+                break                      # cut STEPS, never the fragment size
+    if limiter is not None:
+        limiter.restore_original_limits()
     kind = "reference" if use_ref else "port"
-    sample = ("%d fragments x %d pts per step in %d threads; pyramid = %s, encoder = numpy fp32 restatement "
-              "of the TF1 graph (TensorFlow not installable)") % (
-        T, n_points, T, "reference C++ cores (oracle/_ref)" if use_ref else "C restatement (oracle/liboracle.so)")
-    return value, ms, dict(kind=kind, cores=nproc, threads=T, sample=sample)
+    n_pts = int(sum(c.shape[0] for c in clouds))
+    sample = ("%d fragment(s), %d level-0 pts per step, %d worker threads x %s BLAS threads on %d cores, %d timed steps "
+              "after %d warm-up (median); pyramid = %s, encoder = numpy fp32 restatement of the TF1 graph "
+              "(TensorFlow not installable)") % (
+        len(clouds), n_pts, T, str(blas), nproc, len(times), warmup,
+        "reference C++ cores (oracle/_ref)" if use_ref else "C restatement (oracle/liboracle.so)")
+    return times, dict(kind=kind, cores=nproc, threads=T, sample=sample, points_per_step=n_pts)
+
+
+def cpu_micro_run(P, steps, warmup):
+    """configs[4] on the host: the reference's grid_subsampling + batch_nanoflann_neighbors (single thread each, as one
+    TF op executes)."""
+    from oracle import native as on
+    use_ref = on.have_ref()
+    sub = on.ref_batch_subsampling if use_ref else on.port_batch_subsampling
+    nbf = on.ref_batch_neighbors if use_ref else on.port_batch_neighbors
+    n = np.array([P.shape[0]], np.int32)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        sp, sb = sub(P, n, 0.03)
+        nbf(sp, sp, sb, sb, 0.075)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, dict(kind="reference" if use_ref else "port", cores=os.cpu_count() or 1, threads=1,
+                       sample="1 000 000 raw points per step: grid subsampling dl 0.03 then radius neighbours r 0.075 of "
+                              "the subsampled cloud, single host thread (one TF op), %d timed steps after %d warm-up "
+                              "(median)" % (len(times), warmup), points_per_step=int(P.shape[0]))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -114,8 +203,8 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", os.environ.get("D3F_BENCH_LMS", "20")], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
+                                       "--format=csv,noheader,nounits", "-lms", os.environ.get("D3F_BENCH_LMS", "20")],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
 
@@ -146,31 +235,53 @@ class ClockSampler:
         return out
 
 
+def stats_ms(ts):
+    a = np.asarray(ts, np.float64)
+    return dict(median=float(np.median(a)), mean=float(a.mean()), max=float(a.max()), min=float(a.min()))
+
+
+def measured_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set
+    full` capture (profiles/r2_traffic.json, written by scripts/ncu_summarize.py from the .ncu-rep); null when no
+    capture of the current kernel is committed -- never a hand-copied constant."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(key)
+    if not d:
+        return None, None
+    return int(d["dram_bytes_per_launch"]), d.get("source")
+
+
 # ----------------------------------------------------------------------------------------------------
 def main():
     args = parse()
-    from d3feat_b200 import synth
-    cfg = synth.Config(architecture=synth.ARCH_ENCODER)
-    params = synth.make_params(cfg, seed=0)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = "%d stacked 3DMatch-shaped synthetic fragments x %d pts per GPU, full 5-level KPFCNN encoder" % (
-        args.fragments, args.points)
+    if args.workload == "micro1m":
+        return main_micro(args, world, rank, local_rank)
+    from d3feat_b200 import synth
+    cfg, LIMITS, clouds, wdesc, pseed = make_workload(args.workload, rank)
+    params = synth.make_params(cfg, seed=pseed)
+    config = dict(wdesc, parallelism="fragments sharded, dp%d" % args.gpus)
     base = dict(metric="points/sec through KPFCNN encoder", unit="points/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic",
-                config=dict(workload=workload, fragments_per_gpu=args.fragments, points_per_fragment=args.points,
-                            levels=5, K=15, neighbor_cols=LIMITS, first_subsampling_dl=0.03,
-                            parallelism="fragments sharded, dp%d" % args.gpus))
+                data="synthetic", config=config)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: shrink the fragment when many steps are requested so the arm ends within minutes
-        n_pts = args.points if (args.steps + args.warmup) <= 8 else max(4000, int(args.points * 8 / (args.steps + args.warmup)))
-        value, ms, info = cpu_reference_run(cfg, params, n_pts, args.steps, args.warmup)
-        line = dict(base, impl="reference", value=value, ms_per_step=ms,
+        # the same fragments ALL ranks of the CUDA arm process in one step (N x fragments_per_gpu), on this host's cores
+        all_clouds = []
+        for r in range(max(args.gpus, 1)):
+            all_clouds += make_workload(args.workload, r)[2]
+        times, info = cpu_reference_run(cfg, params, all_clouds, LIMITS, args.steps, min(args.warmup, 2),
+                                        REF_ARM_BUDGET_S)
+        st = stats_ms([t * 1000.0 for t in times])
+        value = info["points_per_step"] / (st["median"] / 1000.0)
+        line = dict(base, impl="reference", value=value, ms_per_step=st["median"], ms_per_step_mean=st["mean"],
+                    ms_per_step_max=st["max"], steps_run=len(times),
                     cpu_baseline=dict(value=value, unit="points/s", cores=info["cores"], kind=info["kind"],
                                       sample=info["sample"]),
                     e2e=dict(value=value, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -193,8 +304,6 @@ def main():
     _lib.lib()
 
     # ---- workload: this rank's fragments (seeded by global fragment id) --------------------------------
-    frag_ids = [rank * args.fragments + i for i in range(args.fragments)]
-    clouds = [synth.room_fragment(f, args.points) for f in frag_ids]
     P = np.concatenate(clouds, 0)
     L = np.array([c.shape[0] for c in clouds], np.int32)
     n_points = int(P.shape[0])
@@ -232,33 +341,37 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(ms):
+        if world > 1:
+            tms = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            return float(tms.item())
+        return ms
+
     def timed(fn, steps, warmup):
+        """One batch at a time. Per-step device time from CUDA events on the launching (current) stream."""
         for _ in range(warmup):
             fn()
         barrier()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         n0 = _lib.launch_count()
-        t0 = time.perf_counter()
         for a, b in evs:
             flush_buf.fill_(1)            # L2 flush between timed iterations (outside the event bracket)
             a.record()
             fn()
             b.record()
         barrier()
-        wall = (time.perf_counter() - t0) * 1000.0 / steps
         launches = (_lib.launch_count() - n0) // max(steps, 1)
-        ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-        if world > 1:
-            tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
-        return ms, wall, launches
+        st = stats_ms([a.elapsed_time(b) for a, b in evs])
+        return st, launches
 
     def timed_pipelined(steps, warmup, e2e):
         """K steps of the two-stream pipeline: encoder(i) on one stream while the pyramid of batch i+1 is built on
         the other (encoder.BatchPipeline). The timed region holds exactly K encoders and K pyramids (the first
         encoder consumes the primed pyramid, the last step builds one more), the L2 flush of every step, and for
-        e2e the H2D copy of each batch's points and the D2H copy of each batch's descriptors."""
+        e2e the H2D copy of each batch's points and the D2H copy of each batch's descriptors. Per-step device time =
+        the interval between consecutive end-of-step events on the encoder stream (the stream every step's last
+        kernel / D2H copy is enqueued on); their sum is the device time of the whole region."""
         from d3feat_b200.encoder import BatchPipeline
 
         def post(inputs, desc):
@@ -271,14 +384,16 @@ def main():
         src_p, src_l, src_bbox = (P_pin, L_pin, None) if e2e else (P_dev, L_dev, bbox)
         host_out = None
 
-        def one(k_flush):
+        def one(k_flush, mark=None):
             nonlocal host_out
             res = pipe.step(src_p, src_l, src_bbox, pre=(lambda: flush_buf.fill_(1)) if k_flush else None)
-            if e2e:
-                with torch.cuda.stream(pipe.s_enc):
+            with torch.cuda.stream(pipe.s_enc):
+                if e2e:
                     if host_out is None:
                         host_out = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
                     host_out.copy_(res, non_blocking=True)
+                if mark is not None:
+                    mark.record(pipe.s_enc)
             return res
 
         pipe.prime(src_p, src_l, src_bbox)
@@ -299,96 +414,257 @@ def main():
         pipe.drain()
         barrier()
         n0 = _lib.launch_count()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         t0 = time.perf_counter()
-        marks = []
-        for _ in range(steps):
-            one(True)
-            marks.append(time.perf_counter())
+        marks[0].record(pipe.s_enc)
+        for i in range(steps):
+            one(True, marks[i + 1])
         pipe.drain()
         barrier()
-        ms = (time.perf_counter() - t0) * 1000.0 / steps      # synchronised on both sides: device-bound wall time
-        step_marks.append([round((b - a) * 1000.0, 2) for a, b in zip([t0] + marks[:-1], marks)])
+        wall = (time.perf_counter() - t0) * 1000.0 / steps      # synchronised on both sides
+        per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
         launches = (_lib.launch_count() - n0) // max(steps, 1)
-        if world > 1:
-            tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-            ms = float(tms.item())
-        return ms, launches
+        st = stats_ms(per_step)
+        st["wall_mean"] = wall
+        return st, launches
 
-    step_marks = []        # host-side time between consecutive pipeline steps (diagnostic: shows one-off stalls)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    seq_ms, _, _ = timed(step_resident, args.steps, max(args.warmup, 3))      # un-pipelined latency of one batch
+    seq, _ = timed(step_resident, args.steps, max(args.warmup, 3))      # un-pipelined latency of one batch
     if args.no_pipeline:
-        ms, wall_ms, launches = timed(step_resident, args.steps, 1)
+        st, launches = timed(step_resident, args.steps, 1)
         clocks = sampler.stop() if sampler else None
-        ms_e2e, wall_e2e, _ = timed(step_e2e, args.steps, 1)
+        st_e2e, _ = timed(step_e2e, args.steps, 1)
     else:
-        ms, launches = timed_pipelined(args.steps, max(args.warmup, 3), False)
-        wall_ms = ms
+        st, launches = timed_pipelined(args.steps, max(args.warmup, 3), False)
         clocks = sampler.stop() if sampler else None
-        ms_e2e, _ = timed_pipelined(args.steps, max(args.warmup, 3), True)
+        st_e2e, _ = timed_pipelined(args.steps, max(args.warmup, 3), True)
+    # headline = the MEDIAN step (max over ranks); mean and max are reported beside it: a single host stall moves the
+    # mean of 20 steps by tens of percent and says nothing about the path
+    ms = reduce_max(st["median"])
+    ms_e2e = reduce_max(st_e2e["median"])
     total_points = n_points * world
     value = total_points / (ms / 1000.0)
     e2e_value = total_points / (ms_e2e / 1000.0)
     d2h = int(step_e2e().numel() * 4)      # bytes of the host tensor the e2e step returns (per rank)
 
-    # ---- roofline of the dominant kernel: the largest KPConv (level 0, 32 -> 32 on all level-0 points) --
+    # ---- roofline: the dominant KPConv timed alone + the whole step against SURVEY 8(d)'s algorithmic bytes --------
     roof = None
     if rank == 0:
-        out = enc(P_dev, L_dev, bbox=bbox, decoder=False)
+        calls = []
+        orig_kp, orig_kd, orig_un, orig_up = co.KPConv_ops, co.KPConv_deform_ops, co.unary_convolution, \
+            co.unary_pair_convolution
+
+        def hook_kp(q, s, idx, f, Kp, W, *a, **k):
+            calls.append(("kpconv", (q, s, idx, f, Kp, W) + a, k))
+            return orig_kp(q, s, idx, f, Kp, W, *a, **k)
+
+        def hook_kd(q, s, idx, f, Kp, off, mod, W, *a, **k):
+            calls.append(("kpconv_deform", (q, s, idx, f, Kp, off, mod, W) + a, k))
+            return orig_kd(q, s, idx, f, Kp, off, mod, W, *a, **k)
+
+        def hook_un(x, w, **k):
+            calls.append(("unary", (x, w), k))
+            return orig_un(x, w, **k)
+
+        def hook_up(x1, w1, a1, x2, w2, a2, alpha):
+            calls.append(("unary_pair", (x1, w1, x2, w2), {}))
+            return orig_up(x1, w1, a1, x2, w2, a2, alpha)
+
+        co.KPConv_ops, co.KPConv_deform_ops, co.unary_convolution, co.unary_pair_convolution = \
+            hook_kp, hook_kd, hook_un, hook_up
+        try:
+            out = enc(P_dev, L_dev, bbox=bbox, decoder=False)
+        finally:
+            co.KPConv_ops, co.KPConv_deform_ops, co.unary_convolution, co.unary_pair_convolution = \
+                orig_kp, orig_kd, orig_un, orig_up
         inp = out["inputs"]
-        q = inp["points"][0]
-        idx = inp["neighbors"][0]
-        Nq, H = idx.shape
-        feat = torch.randn((Nq, 32), device=dev)
-        Kp = enc.store.get("layer_0/resnetb_1/conv2/kernel_points")
-        W = enc.store.get("layer_0/resnetb_1/conv2/weights")
-        extent = cfg.KP_extent * (cfg.first_subsampling_dl * cfg.density_parameter) / cfg.density_parameter
+        enc_bytes, best = 0, None
+        for kind, a, k in calls:
+            if kind in ("kpconv", "kpconv_deform"):
+                idx, f, W = a[2], a[3], (a[5] if kind == "kpconv" else a[7])
+                b = kpconv_algorithmic_bytes(int(idx.shape[0]), int(idx.shape[1]), int(W.shape[0]), int(W.shape[1]),
+                                             int(W.shape[2]))
+                if kind == "kpconv" and int(W.shape[1]) > 1 and (best is None or b > best[0]):
+                    best = (b, a, k)
+            elif kind == "unary":
+                b = unary_algorithmic_bytes(int(a[0].shape[0]), int(a[1].shape[0]), int(a[1].shape[1]),
+                                            k.get("residual") is not None)
+            else:
+                b = (unary_algorithmic_bytes(int(a[0].shape[0]), int(a[1].shape[0]), int(a[1].shape[1])) +
+                     4 * int(a[2].shape[0]) * int(a[2].shape[1]) + 4 * int(a[3].shape[0]) * int(a[3].shape[1]))
+            enc_bytes += b
+        sizes = [int(p.shape[0]) for p in inp["points"]]
+        pyr_bytes = 0
+        for l in range(len(sizes)):
+            pyr_bytes += neighbors_algorithmic_bytes(sizes[l], sizes[l], LIMITS[l])
+            if l + 1 < len(sizes):
+                pyr_bytes += subsample_algorithmic_bytes(sizes[l], sizes[l + 1])
+                pyr_bytes += neighbors_algorithmic_bytes(sizes[l + 1], sizes[l], LIMITS[l])
+                pyr_bytes += neighbors_algorithmic_bytes(sizes[l], sizes[l + 1], LIMITS[l])
+        abytes, a, k = best
         for _ in range(3):
-            co.KPConv_ops(q, q, idx, feat, Kp, W, extent, "linear", "sum")
+            orig_kp(*a, **k)
         reps = 10
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:
+        for ea, eb in evs:
             flush_buf.fill_(1)
-            a.record()
-            co.KPConv_ops(q, q, idx, feat, Kp, W, extent, "linear", "sum")
-            b.record()
+            ea.record()
+            orig_kp(*a, **k)
+            eb.record()
         torch.cuda.synchronize()
-        kms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
-        abytes = kpconv_algorithmic_bytes(Nq, H, 15, 32, 32)
+        kst = stats_ms([ea.elapsed_time(eb) for ea, eb in evs])
+        kms = kst["median"]
+        Nq, H = int(a[2].shape[0]), int(a[2].shape[1])
+        Cin, Cout = int(a[5].shape[1]), int(a[5].shape[2])
         peak, peak_src = peaks()
         ach = abytes / (kms * 1e-3) / 1e9
-        # DRAM bytes of the op from the committed ncu capture (profiles/r1_v4_ncu_metrics.txt), per 21760-query chunk:
-        # stage-1 kernel 8.07 MB read + 0.33 MB written (the gathered rows are L2 hits), contraction 42.04 MB read
-        # (the chunk's wf -- ncu flushes L2 between kernels; back to back it is an L2 hit as well)
-        n_chunks = -(-int(Nq) // 21760)
-        traffic = int((8.07e6 + 0.33e6 + 42.04e6) * n_chunks) if (args.fragments, args.points) == (8, 30000) else None
-        roof = dict(bound="hbm", kernel="kpconv level-0 32->32 (mma.sync stage-1 gather/correlation + tcgen05 contraction)", achieved=ach,
-                    peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, peak_source=peak_src,
-                    algorithmic_bytes_per_launch=abytes, ms_per_launch=kms, Nq=int(Nq), H=int(H))
+        traffic, traffic_src = measured_traffic("kpconv_%d_%d" % (Cin, Cout))
+        whole = (enc_bytes + pyr_bytes) / (st["median"] * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel="KPConv %d->%d on Nq=%d queries x H=%d (d3f_kpconv_forward, the largest KPConv "
+                                        "of the step)" % (Cin, Cout, Nq, H),
+                    achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic, traffic_source=traffic_src,
+                    peak_source=peak_src, algorithmic_bytes_per_launch=abytes, ms_per_launch=kms,
+                    ms_per_launch_max=kst["max"], Nq=Nq, H=H,
+                    whole_step=dict(algorithmic_bytes=int(enc_bytes + pyr_bytes), encoder_bytes=int(enc_bytes),
+                                    pyramid_bytes=int(pyr_bytes), achieved=whole, frac=whole / peak,
+                                    note="SURVEY 8(d) gather model summed over every KPConv / unary / neighbour search "
+                                         "/ subsampling of one step, divided by the median step time"),
+                    whole_step_frac=whole / peak)
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
-        v, cms, info = cpu_reference_run(cfg, params, args.points, 1, 0)
-        cpu = dict(value=v, unit="points/s", cores=info["cores"], kind=info["kind"], sample=info["sample"],
-                   ms_per_step=cms)
+        # same fragments as the timed CUDA step, 1 warm-up + 3 timed steps, median
+        times, info = cpu_reference_run(cfg, params, clouds, LIMITS, 3, 1, 120.0)
+        cst = stats_ms([t * 1000.0 for t in times])
+        cpu = dict(value=info["points_per_step"] / (cst["median"] / 1000.0), unit="points/s", cores=info["cores"],
+                   kind=info["kind"], sample=info["sample"], ms_per_step=cst["median"], ms_per_step_max=cst["max"])
 
     if rank == 0:
-        line = dict(base, value=value, ms_per_step=ms, wall_ms_per_step=wall_ms,
+        line = dict(base, value=value, ms_per_step=ms, ms_per_step_mean=st["mean"], ms_per_step_max=st["max"],
+                    wall_ms_per_step=st.get("wall_mean", st["mean"]),
                     e2e=dict(value=e2e_value, unit="points/s", h2d_bytes_per_step=int(P.nbytes + L.nbytes) * world,
-                             d2h_bytes_per_step=d2h, ms_per_step=ms_e2e),
+                             d2h_bytes_per_step=d2h * world, ms_per_step=ms_e2e, ms_per_step_mean=st_e2e["mean"],
+                             ms_per_step_max=st_e2e["max"]),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu)
-        line["config"]["l2"] = "256 MiB L2 flush at the start of every timed step"
-        line["config"]["e2e_output"] = ("every rank returns its own fragments' descriptors to its host; with N > 1 the "
-                                        "all-gathered matrix stays in HBM")
-        line["config"]["pipeline"] = ("one batch at a time" if args.no_pipeline else
-                                      "two streams: pyramid(i+1) || encoder(i) (encoder.BatchPipeline)")
-        line["single_batch_latency_ms"] = seq_ms
-        if step_marks:
-            line["pipeline_host_step_ms"] = dict(resident=step_marks[0], e2e=step_marks[-1])
+        line["detail"] = dict(
+            statistic="value / e2e = points per MEDIAN step (max over ranks); mean and max beside it",
+            l2="256 MiB L2 flush at the start of every timed step",
+            e2e_output="every rank returns its own fragments' descriptors to its host; with N > 1 the all-gathered "
+                       "matrix stays in HBM",
+            pipeline=("one batch at a time" if args.no_pipeline else
+                      "two streams: pyramid(i+1) || encoder(i) (encoder.BatchPipeline)"))
+        line["single_batch_latency_ms"] = seq["median"]
+        line["single_batch_latency_ms_max"] = seq["max"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+#  configs[4]: 1 M-point radius-neighbour + grid-subsample microbench
+# ----------------------------------------------------------------------------------------------------
+def main_micro(args, world, rank, local_rank):
+    from d3feat_b200 import synth
+    P = synth.surface_cloud(rank, 1000000)
+    config = dict(workload="radius-neighbour (r 0.075) + grid-subsample (dl 0.03) microbench, 1 000 000 raw points per "
+                           "GPU, hash-grid kernels", baseline_config="configs[4]", points=1000000, dl=0.03,
+                  radius=0.075, parallelism="replicas, dp%d" % args.gpus)
+    base = dict(metric="points/sec through grid subsampling + radius neighbours", unit="points/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=config)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        times, info = cpu_micro_run(P, min(args.steps, 5), min(args.warmup, 1))
+        st = stats_ms([t * 1000.0 for t in times])
+        value = info["points_per_step"] / (st["median"] / 1000.0)
+        print(json.dumps(dict(base, impl="reference", value=value, ms_per_step=st["median"], steps_run=len(times),
+                              cpu_baseline=dict(value=value, unit="points/s", cores=info["cores"], kind=info["kind"],
+                                                sample=info["sample"]),
+                              e2e=dict(value=value, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                              gpu_launches=0)))
+        return
+    import torch
+    from d3feat_b200 import _lib, tf_custom_ops as ops
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.lib()
+    P_pin = torch.from_numpy(P).pin_memory()
+    P_dev = P_pin.to(dev)
+    n_dev = torch.tensor([P.shape[0]], dtype=torch.int32, device=dev)
+    bbox = np.concatenate([P.min(0), P.max(0)]).astype(np.float32)
+    flush_buf = torch.empty((256 << 20,), dtype=torch.uint8, device=dev)
+    res = {}
+
+    def sub(p):
+        return ops.batch_grid_subsampling(p, n_dev, 0.03, bbox=bbox)
+
+    def nbr(sp, sb):
+        return ops.batch_ordered_neighbors(sp, sp, sb, sb, 0.075, bbox=bbox)
+
+    def step(p):
+        sp, sb = sub(p)
+        nb = nbr(sp, sb)
+        res["M"], res["cols"] = int(sp.shape[0]), int(nb.shape[1])
+        return sp, sb, nb
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        n0 = _lib.launch_count()
+        for a, b in evs:
+            flush_buf.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return stats_ms([a.elapsed_time(b) for a, b in evs]), (_lib.launch_count() - n0) // max(steps, 1)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    st, launches = timed(lambda: step(P_dev), args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if sampler else None
+
+    def e2e():
+        sp, sb, nb = step(P_pin.to(dev, non_blocking=True))
+        return sp.cpu(), nb.cpu()
+    st_e2e, _ = timed(e2e, max(3, args.steps // 2), 2)
+    sp, sb, nb = step(P_dev)
+    M, cols = res["M"], res["cols"]
+    st_sub, _ = timed(lambda: sub(P_dev), args.steps, 2)
+    st_nb, _ = timed(lambda: nbr(sp, sb), args.steps, 2)
+    peak, peak_src = peaks()
+    nb_bytes = neighbors_algorithmic_bytes(M, M, cols)
+    sub_bytes = subsample_algorithmic_bytes(P.shape[0], M)
+    ach = nb_bytes / (st_nb["median"] * 1e-3) / 1e9
+    traffic, traffic_src = measured_traffic("radius_query_1m")
+    roof = dict(bound="hbm", kernel="radius neighbours of %d subsampled points, %d columns (hash-grid build + query)" % (
+                    M, cols), achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=traffic,
+                traffic_source=traffic_src, peak_source=peak_src, algorithmic_bytes_per_launch=int(nb_bytes),
+                ms_per_launch=st_nb["median"],
+                subsample=dict(algorithmic_bytes=int(sub_bytes), ms=st_sub["median"],
+                               achieved=sub_bytes / (st_sub["median"] * 1e-3) / 1e9,
+                               frac=sub_bytes / (st_sub["median"] * 1e-3) / 1e9 / peak),
+                whole_step_frac=(nb_bytes + sub_bytes) / (st["median"] * 1e-3) / 1e9 / peak)
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        times, info = cpu_micro_run(P, 3, 1)
+        cst = stats_ms([t * 1000.0 for t in times])
+        cpu = dict(value=info["points_per_step"] / (cst["median"] / 1000.0), unit="points/s", cores=info["cores"],
+                   kind=info["kind"], sample=info["sample"], ms_per_step=cst["median"])
+    if rank == 0:
+        n = P.shape[0] * world
+        print(json.dumps(dict(base, value=n / (st["median"] * 1e-3), ms_per_step=st["median"],
+                              ms_per_step_mean=st["mean"], ms_per_step_max=st["max"],
+                              e2e=dict(value=n / (st_e2e["median"] * 1e-3), unit="points/s",
+                                       h2d_bytes_per_step=int(P.nbytes) * world,
+                                       d2h_bytes_per_step=int(12 * M + 4 * M * cols) * world,
+                                       ms_per_step=st_e2e["median"]),
+                              gpu_launches=int(launches), clocks=clocks, roofline=roof, cpu_baseline=cpu,
+                              detail=dict(subsampled_points=M, neighbor_cols=cols,
+                                          l2="256 MiB L2 flush at the start of every timed step"))))
 
 
 if __name__ == "__main__":

@@ -1,0 +1,290 @@
+"""GPU parity at BASELINE.json's REAL configurations (the shapes bench.py measures), not at reduced sizes:
+
+* configs[1] / configs[3] -- bench.py's exact workload: 8 stacked room_fragment(f, 30000), 40 neighbour columns.
+  Pyramid: every matrix bit-exact against the oracle pyramid built with the REFERENCE's compiled C++ cores
+  (oracle/_ref, canonicalised; the C port when _ref is absent). Encoder: the float64 restatement of the whole
+  encoder for one 30k-point fragment (<= 1e-4 per level), and a sampled-row oracle check of every fused op of the
+  full 8 x 30k batch.
+* configs[4] -- 1 M points: grid subsampling and radius neighbours bit-exact against the reference C++ cores.
+* configs[2] -- KITTI parameters (first_subsampling_dl 0.30, results_kitti/Log_11011605/parameters.txt) against
+  the full float64 restatement, and the 120k-point scan against the restatement on >= 2000 sampled query rows of
+  every KPConv (rigid, offset head and deformable) and every unary / pool.
+
+Tolerances: bit-exact on indices and barycenters; 1e-4 max-norm relative per tensor on fp32 features (north_star).
+Reference files followed: datasets/common.py:1301-1413, tf_custom_ops/tf_neighbors/neighbors/neighbors.cpp:211-332,
+tf_custom_ops/tf_subsampling/grid_subsampling/grid_subsampling.cpp:5-149, kernels/convolution_ops.py:161-499,
+models/network_blocks.py:1052-1118.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import native as on
+from oracle import kpconv_np as ok
+
+from _trace import record_ops, check_sampled_rows
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+BENCH_LIMITS = [40, 40, 40, 40, 40]          # bench.py LIMITS
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+# ---- the reference's C++ cores, canonicalised -----------------------------------------------------------
+# The reference emits subsampled cells in std::unordered_map iteration order and breaks exact-d2 ties by KD-tree
+# visit order (hard parts 1-2). Canonical forms: cells ascend in the reference's cell key per cloud (= the
+# C port's order), neighbours ascend in (d2, index). Feeding every level with canonically ordered points makes the
+# reference's in-input-order fp32 barycenter sums identical to ours, level after level.
+
+def canonical_ref_subsampling(points, lengths, dl):
+    rp, rb = on.ref_batch_subsampling(points, lengths, dl)
+    pp, pb = on.port_batch_subsampling(points, lengths, dl)
+    assert np.array_equal(rb, pb)
+    o = 0
+    for n in rb:                                   # same point SET per cloud, bit for bit
+        a, _ = on.sort_rows(bits(rp[o:o + n]))
+        b, _ = on.sort_rows(bits(pp[o:o + n]))
+        assert np.array_equal(a, b)
+        o += n
+    return pp, pb
+
+
+def canonical_ref_neighbors(q, s, qb, sb, r):
+    nbm = on.ref_batch_neighbors(q, s, qb, sb, r)
+    canon, _ = on.canonicalize_neighbors(nbm, q, s, s.shape[0])
+    return canon
+
+
+def oracle_native_fns():
+    if on.have_ref():
+        return canonical_ref_neighbors, canonical_ref_subsampling, "reference C++ cores (oracle/_ref)"
+    return on.port_batch_neighbors, on.port_batch_subsampling, "C port (oracle/_ref absent)"
+
+
+def assert_pyramid_equal(inputs, ref, L):
+    for l in range(L):
+        assert np.array_equal(bits(inputs["points"][l]), bits(ref["points"][l])), "points level %d" % l
+        assert np.array_equal(inputs["lengths"][l], ref["lengths"][l]), "lengths level %d" % l
+        for key in ("neighbors", "pools", "upsamples"):
+            a, b = inputs[key][l], ref[key][l]
+            if b.shape[0] == 0:
+                assert a.shape[0] == 0
+                continue
+            sup = {"neighbors": l, "pools": l, "upsamples": l + 1}[key]
+            shadow = ref["points"][sup].shape[0]
+            if b.shape[1] < a.shape[1]:             # ours is always `limit` wide, the reference slice min(max, limit)
+                b = np.concatenate([b, np.full((b.shape[0], a.shape[1] - b.shape[1]), shadow, np.int32)], 1)
+            assert a.shape == b.shape, (key, l, a.shape, b.shape)
+            assert np.array_equal(a, b), (key, l)
+
+
+def _inputs_to_numpy(out, n_points, in_dim=1):
+    inputs = {k: [x.cpu().numpy() for x in v] for k, v in out["inputs"].items() if k not in ("features", "orders")}
+    inputs["features"] = np.ones((n_points, in_dim), np.float32)
+    return inputs
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  configs[1] / [3]: bench.py's workload
+# ----------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def bench_workload(cuda):
+    """Exactly what bench.py builds for rank 0: fragments 0..7 x 30000 points, ARCH_ENCODER, seed-0 parameters."""
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN
+    cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+    params = synth.make_params(cfg, seed=0)
+    clouds = [synth.room_fragment(f, 30000) for f in range(8)]
+    P = np.concatenate(clouds, 0)
+    L = np.array([c.shape[0] for c in clouds], np.int32)
+    enc = KPFCNN(cfg, params, BENCH_LIMITS, device=cuda)
+    return cfg, params, clouds, P, L, enc
+
+
+def test_bench_workload_pyramid_bit_exact_vs_reference_cores(cuda, bench_workload):
+    cfg, params, clouds, P, L, enc = bench_workload
+    assert P.shape[0] == 240000
+    out = enc(P, L, decoder=False)
+    inputs = _inputs_to_numpy(out, P.shape[0])
+    nb_fn, sb_fn, which = oracle_native_fns()
+    ref = ok.descriptor_input_pyramid(cfg, P, L, BENCH_LIMITS, nb_fn, sb_fn)
+    assert [p.shape[0] for p in ref["points"]] == [p.shape[0] for p in inputs["points"]], which
+    assert_pyramid_equal(inputs, ref, 5)
+
+
+def test_bench_workload_encoder_one_fragment_vs_float64(cuda, bench_workload):
+    """One 30k-point fragment (BASELINE configs[1] literally) through the full 5-level encoder, 40 columns, vs the
+    float64 restatement on the same pyramid: every level's skip features and the final [N4, 2048] features."""
+    cfg, params, clouds, P, L, enc = bench_workload
+    c = clouds[3]
+    l1 = np.array([c.shape[0]], np.int32)
+    out = enc(c, l1, decoder=False)
+    inputs = _inputs_to_numpy(out, c.shape[0])
+    F_ref = ok.EncoderOracle(cfg, params, np.float64).encoder(inputs)
+    assert [f.shape[1] for f in out["F"]] == [128, 256, 512, 1024, 2048]
+    for l, (a, b) in enumerate(zip(out["F"], F_ref)):
+        assert a.shape == b.shape
+        assert rel_err(a.cpu().numpy(), b) < RTOL, "level %d" % l
+
+
+def test_bench_workload_every_op_sampled_rows_vs_float64(cuda, bench_workload):
+    """The full 8 x 30k batch (the shape bench.py times): the float64 restatement of every fused op on 2000 sampled
+    output rows, on that op's real inputs."""
+    cfg, params, clouds, P, L, enc = bench_workload
+    with record_ops() as tr:
+        out = enc(P, L, decoder=False)
+        torch.cuda.synchronize()
+    assert out["F"][-1].shape[1] == 2048
+    rep = check_sampled_rows(tr, 2000, np.random.default_rng(0), RTOL, min_kpconv=10)
+    assert sum(1 for r in rep if r[0] in ("unary", "unary_pair")) >= 18
+    # the single-shot result equals the pipelined one bit for bit (BatchPipeline is what bench.py times)
+    from d3feat_b200.encoder import BatchPipeline
+    pipe = BatchPipeline(enc, decoder=False)
+    pipe.prime(t(P, cuda), t(L, cuda))
+    res = pipe.step(None, None)
+    pipe.drain()
+    assert torch.equal(res, out["F"][-1])
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  configs[4]: 1 M-point microbench, bit-exact vs the reference C++ cores
+# ----------------------------------------------------------------------------------------------------------
+
+def test_micro_1m_bit_exact_vs_reference_cores(cuda):
+    from d3feat_b200 import synth, tf_custom_ops as ops
+    if not on.have_ref():
+        pytest.skip("oracle/_ref (the compiled reference cores) is not present")
+    P = synth.surface_cloud(0, 1000000)
+    n = np.array([P.shape[0]], np.int32)
+    sp, sb = ops.batch_grid_subsampling(t(P, cuda), t(n, cuda), 0.03)
+    rp, rb = on.ref_batch_subsampling(P, n, 0.03)              # std::unordered_map order
+    M = int(rb[0])
+    assert sp.shape[0] == M and int(sb.item()) == M
+    ours = bits(sp.cpu().numpy())
+    a, _ = on.sort_rows(ours)
+    b, _ = on.sort_rows(bits(rp))
+    assert np.array_equal(a, b)                                # same barycenters, bit for bit
+    # canonical order == ascending reference cell key
+    mn = P.min(0)
+    dl = np.float32(0.03)
+    org = np.floor(mn * np.float32(1 / dl)) * dl                # grid_subsampling.cpp:25-31
+    spc = sp.cpu().numpy()
+    # radius neighbours of the subsampled cloud (r = 0.075), every row, vs the reference's KD-tree search
+    m = np.array([M], np.int32)
+    nbm = ops.batch_ordered_neighbors(sp, sp, t(m, cuda), t(m, cuda), 0.075).cpu().numpy()
+    ref = on.ref_batch_neighbors(spc, spc, m, m, 0.075)
+    assert nbm.shape == ref.shape                               # same maximum count
+    canon, _ = on.canonicalize_neighbors(ref, spc, spc, M)
+    assert np.array_equal(nbm, canon)
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  configs[2]: KITTI-shaped scan, deformable blocks
+# ----------------------------------------------------------------------------------------------------------
+
+def test_kitti_reference_parameters_dl030_vs_float64(cuda):
+    """The reference's KITTI parameters (first_subsampling_dl = 0.30 -> conv radius 0.75 m, deformable blocks in the
+    last two levels with the doubled search radius): whole encoder vs the float64 restatement."""
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN
+    cfg = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.30, first_features_dim=32)
+    cloud = synth.lidar_scan(2, 16000, dl=0.30)
+    L = np.array([cloud.shape[0]], np.int32)
+    params = synth.make_params(cfg, 2)
+    limits = [40, 40, 40, 60, 40]
+    out = KPFCNN(cfg, params, limits, device=cuda)(cloud, L)
+    inputs = _inputs_to_numpy(out, cloud.shape[0])
+    nb_fn, sb_fn, which = oracle_native_fns()
+    ref = ok.descriptor_input_pyramid(cfg, cloud, L, limits, nb_fn, sb_fn)
+    assert_pyramid_equal(inputs, ref, len(ref["points"]))
+    F_ref = ok.EncoderOracle(cfg, params, np.float64).encoder(inputs)
+    for l, (a, b) in enumerate(zip(out["F"], F_ref)):
+        assert rel_err(a.cpu().numpy(), b) < RTOL, "level %d" % l
+
+
+def test_kitti_120k_every_op_sampled_rows_vs_float64(cuda):
+    """120 000 level-0 points (BASELINE configs[2]'s size; reached with a 4 cm first voxel, a 64-beam scan voxelised at
+    0.30 m keeps < 25k points): pyramid bit-exact vs the reference cores, and every KPConv -- rigid, offset head,
+    deformable -- unary and pool on 2000 sampled rows vs the float64 restatement."""
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN
+    cfg = synth.Config(architecture=synth.ARCH_KITTI_DEFORM, first_subsampling_dl=0.04, first_features_dim=32)
+    cloud = synth.lidar_scan(1, 120000, dl=0.04)
+    L = np.array([cloud.shape[0]], np.int32)
+    params = synth.make_params(cfg, 1)
+    limits = [40, 40, 40, 60, 40]
+    enc = KPFCNN(cfg, params, limits, device=cuda)
+    with record_ops() as tr:
+        out = enc(cloud, L)
+        torch.cuda.synchronize()
+    inputs = _inputs_to_numpy(out, cloud.shape[0])
+    nb_fn, sb_fn, which = oracle_native_fns()
+    ref = ok.descriptor_input_pyramid(cfg, cloud, L, limits, nb_fn, sb_fn)
+    assert_pyramid_equal(inputs, ref, len(ref["points"]))
+    rep = check_sampled_rows(tr, 2000, np.random.default_rng(1), RTOL, min_kpconv=10)
+    assert any(r[0] == "kpconv_deform" for r in rep)
+    # reproducible: no atomics on float data anywhere on the path
+    F2 = enc(cloud, L)["F"]
+    for a, b in zip(out["F"], F2):
+        assert torch.equal(a, b)
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  num_kernel_points other than 15 (utils/config.py allows any K) and the pipeline's stream contract
+# ----------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("K,Cin,Cout,deform", [(7, 32, 32, False), (19, 16, 24, False), (13, 32, 48, True)])
+def test_kpconv_any_number_of_kernel_points(cuda, K, Cin, Cout, deform):
+    from d3feat_b200 import convolution_ops as co
+    from test_gpu_kpconv import make_case
+    rng = np.random.default_rng(K)
+    q, s, idx, f, Kp, W = make_case(rng, 700, 700, 45, Cin, Cout, K=K, extent=0.1)
+    args = [t(x, cuda) for x in (q, s, idx, f, Kp)]
+    if deform:
+        off = (rng.normal(size=(700, K, 3)) * 0.03).astype(np.float32)
+        out = co.KPConv_deform_ops(*args, t(off, cuda), None, t(W, cuda), 0.1, "linear", "sum").cpu().numpy()
+        ref = ok.kpconv_deform_ops(q, s, idx, f, Kp, off, None, W, 0.1, "linear", "sum", dtype=np.float64)
+    else:
+        for mode in ("sum", "closest"):
+            out = co.KPConv_ops(*args, t(W, cuda), 0.1, "linear", mode).cpu().numpy()
+            ref = ok.kpconv_ops(q, s, idx, f, Kp, W, 0.1, "linear", mode, dtype=np.float64)
+            assert rel_err(out, ref) < RTOL, mode
+    assert rel_err(out, ref) < RTOL
+
+
+def test_batch_pipeline_result_is_ordered_on_the_callers_stream(cuda):
+    """BatchPipeline.step() returns a tensor produced on its private stream; the caller's current stream must see
+    finished data without any explicit synchronisation."""
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN, BatchPipeline
+    cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+    params = synth.make_params(cfg, 5)
+    enc = KPFCNN(cfg, params, [35, 33, 34, 36, 30], device=cuda)
+    c = synth.room_fragment(90, 20000)
+    L = np.array([c.shape[0]], np.int32)
+    want = enc(c, L, decoder=False)["F"][-1].clone()
+    torch.cuda.synchronize()
+    pipe = BatchPipeline(enc, decoder=False)
+    pipe.prime(t(c, cuda), t(L, cuda))
+    got = []
+    for i in range(4):
+        res = pipe.step(t(c, cuda), t(L, cuda))
+        got.append(res.clone())              # consumer kernel on the caller's (default) stream, no sync in between
+    pipe.drain()
+    for g in got:
+        assert torch.equal(g, want)
