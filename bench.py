@@ -365,6 +365,46 @@ def main():
         st = stats_ms([a.elapsed_time(b) for a, b in evs])
         return st, launches
 
+    def make_pipeline(post):
+        """(pipeline, step(points, lengths, bbox, pre) -> result tensor). Default: GraphPipeline (static pyramid + device
+        row counts, the step = two CUDA graph replays); --no-graph: BatchPipeline (eager launches, 4 size read-backs)."""
+        from d3feat_b200.encoder import BatchPipeline, GraphPipeline
+        if args.no_graph:
+            pipe = BatchPipeline(enc, decoder=False, post=post)
+            return pipe, (lambda p, l, bb, pre: pipe.step(p, l, bb, pre=pre)), (lambda p, l, bb: pipe.prime(p, l, bb))
+        pipe = GraphPipeline.for_batch(enc, P_dev, L_dev, decoder=False, post=post)
+
+        def step(p, l, bb, pre):
+            res, counts = pipe.step(p, l, pre=pre)
+            last_counts[0] = counts
+            return res
+        return pipe, step, (lambda p, l, bb: pipe.prime(p, l))
+
+    last_counts = [None]
+
+    def timed_latency(steps, warmup):
+        """One batch at a time through the same pipeline object (prime -> step -> result on the caller's stream):
+        the un-overlapped latency of a batch."""
+        pipe, step, prime = make_pipeline(None)
+
+        def one():
+            prime(P_dev, L_dev, bbox)
+            return step(None, None, None, None)
+        for _ in range(warmup):
+            one()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush_buf.fill_(1)
+            a.record()
+            one()
+            b.record()
+        pipe.drain()
+        barrier()
+        if hasattr(pipe, "check"):
+            pipe.check()
+        return stats_ms([a.elapsed_time(b) for a, b in evs])
+
     def timed_pipelined(steps, warmup, e2e):
         """K steps of the two-stream pipeline: encoder(i) on one stream while the pyramid of batch i+1 is built on
         the other (encoder.BatchPipeline). The timed region holds exactly K encoders and K pyramids (the first
@@ -372,31 +412,35 @@ def main():
         e2e the H2D copy of each batch's points and the D2H copy of each batch's descriptors. Per-step device time =
         the interval between consecutive end-of-step events on the encoder stream (the stream every step's last
         kernel / D2H copy is enqueued on); their sum is the device time of the whole region."""
-        from d3feat_b200.encoder import BatchPipeline
-
         def post(inputs, desc):
             if world > 1:      # the one exchange step: NCCL all-gather of the per-fragment descriptors (sync-free);
                 # the gathered matrix stays in HBM, the step returns this rank's own descriptors
-                gathered[0], _ = all_gather_descriptors_padded(desc, inputs["lengths"][-1], gather_cap)
+                rows = inputs.get("rows")
+                gathered[0], _ = all_gather_descriptors_padded(desc, inputs["lengths"][-1], max(gather_cap, desc.shape[0]),
+                                                               rows_dev=rows[-1] if rows else None)
             return desc
 
-        pipe = BatchPipeline(enc, decoder=False, post=post)
+        pipe, step, prime = make_pipeline(post)
         src_p, src_l, src_bbox = (P_pin, L_pin, None) if e2e else (P_dev, L_dev, bbox)
         host_out = None
+        host_counts = torch.zeros((8,), dtype=torch.int32).pin_memory()
 
         def one(k_flush, mark=None):
             nonlocal host_out
-            res = pipe.step(src_p, src_l, src_bbox, pre=(lambda: flush_buf.fill_(1)) if k_flush else None)
+            res = step(src_p, src_l, src_bbox, (lambda: flush_buf.fill_(1)) if k_flush else None)
             with torch.cuda.stream(pipe.s_enc):
-                if e2e:
+                if e2e:       # the rank's descriptors (and, graph mode, the device-side level counts) go to the host
                     if host_out is None:
                         host_out = torch.empty(res.shape, dtype=res.dtype, pin_memory=True)
+                        e2e_bytes[0] = int(host_out.numel() * 4) + (32 if last_counts[0] is not None else 0)
                     host_out.copy_(res, non_blocking=True)
+                    if last_counts[0] is not None:
+                        host_counts.copy_(last_counts[0], non_blocking=True)
                 if mark is not None:
                     mark.record(pipe.s_enc)
             return res
 
-        pipe.prime(src_p, src_l, src_bbox)
+        prime(src_p, src_l, src_bbox)
         for _ in range(warmup):
             one(False)
         # untimed settling: a fresh process can see one-off stalls (allocator growth, the previous process's context
@@ -424,12 +468,19 @@ def main():
         wall = (time.perf_counter() - t0) * 1000.0 / steps      # synchronised on both sides
         per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
         launches = (_lib.launch_count() - n0) // max(steps, 1)
+        if hasattr(pipe, "check"):
+            pipe.check()                                          # no batch overflowed the shape bucket
+            launches = int(pipe.kernels_per_step)                 # kernels inside the two replayed graphs of a step
         st = stats_ms(per_step)
         st["wall_mean"] = wall
         return st, launches
 
+    e2e_bytes = [None]
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    seq, _ = timed(step_resident, args.steps, max(args.warmup, 3))      # un-pipelined latency of one batch
+    if args.no_pipeline:
+        seq, _ = timed(step_resident, args.steps, max(args.warmup, 3))      # un-pipelined latency of one batch
+    else:
+        seq = timed_latency(args.steps, max(args.warmup, 3))
     if args.no_pipeline:
         st, launches = timed(step_resident, args.steps, 1)
         clocks = sampler.stop() if sampler else None
@@ -445,7 +496,8 @@ def main():
     total_points = n_points * world
     value = total_points / (ms / 1000.0)
     e2e_value = total_points / (ms_e2e / 1000.0)
-    d2h = int(step_e2e().numel() * 4)      # bytes of the host tensor the e2e step returns (per rank)
+    # bytes of the host tensor(s) the e2e step returns (per rank)
+    d2h = e2e_bytes[0] if e2e_bytes[0] is not None else int(step_e2e().numel() * 4)
 
     # ---- roofline: the dominant KPConv timed alone + the whole step against SURVEY 8(d)'s algorithmic bytes --------
     roof = None
@@ -466,9 +518,9 @@ def main():
             calls.append(("unary", (x, w), k))
             return orig_un(x, w, **k)
 
-        def hook_up(x1, w1, a1, x2, w2, a2, alpha):
+        def hook_up(x1, w1, a1, x2, w2, a2, alpha, **k):
             calls.append(("unary_pair", (x1, w1, x2, w2), {}))
-            return orig_up(x1, w1, a1, x2, w2, a2, alpha)
+            return orig_up(x1, w1, a1, x2, w2, a2, alpha, **k)
 
         co.KPConv_ops, co.KPConv_deform_ops, co.unary_convolution, co.unary_pair_convolution = \
             hook_kp, hook_kd, hook_un, hook_up
@@ -551,8 +603,10 @@ def main():
             l2="256 MiB L2 flush at the start of every timed step",
             e2e_output="every rank returns its own fragments' descriptors to its host; with N > 1 the all-gathered "
                        "matrix stays in HBM",
-            pipeline=("one batch at a time" if args.no_pipeline else
-                      "two streams: pyramid(i+1) || encoder(i) (encoder.BatchPipeline)"))
+            pipeline=("one batch at a time, eager launches" if args.no_pipeline else
+                      ("two streams: pyramid(i+1) || encoder(i), eager launches (encoder.BatchPipeline)" if args.no_graph
+                       else "two streams: pyramid(i+1) || encoder(i); each half is ONE CUDA graph replay per step, level "
+                            "sizes stay on the device, no host synchronisation (encoder.GraphPipeline)")))
         line["single_batch_latency_ms"] = seq["median"]
         line["single_batch_latency_ms_max"] = seq["max"]
         print(json.dumps(line))

@@ -28,23 +28,23 @@ SYMBOLS = [
     ("d3f_radius_neighbors_fill", _I, [_P, _P, _I, _P, _P, _I, _I, _F, _P, _P, _I, _I, _P, _P]),
     ("d3f_kpconv_workspace_bytes", _Z, [_I, _I, _I, _I, _I, _I]),
     ("d3f_pyramid_workspace_bytes", _Z, [_I, _P, _P, _P]),
-    ("d3f_pyramid_build", _I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P]),
+    ("d3f_pyramid_build", _I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _Z, _P, _P, _P, _P]),
     ("d3f_packed_weight_floats", _Z, [_I, _I]),
     ("d3f_pack_weight", _I, [_P, _I, _I, _P, _P]),
     ("d3f_radius_neighbors_order", _I, [_P, _I, _I, _F, _P, _P, _P]),
     ("d3f_kpconv_forward", _I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _I, _P, _P, _P, _F, _P,
-                                _P, _Z, _P]),
+                                _P, _Z, _P, _P, _P]),
     ("d3f_kpconv_deform_forward", _I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _I, _P, _P,
-                                       _P, _F, _P, _P, _Z, _P]),
-    ("d3f_unary_forward", _I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P]),
+                                       _P, _F, _P, _P, _Z, _P, _P, _P]),
+    ("d3f_unary_forward", _I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P]),
     ("d3f_ind_max_pool_workspace_bytes", _Z, [_I]),
-    ("d3f_ind_max_pool", _I, [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
-    ("d3f_closest_pool", _I, [_P, _P, _I, _I, _I, _I, _P, _P]),
-    ("d3f_l2_normalize", _I, [_P, _I, _I, _F, _P, _P]),
-    ("d3f_unary_pair_forward", _I, [_P, _I, _P, _I, _P, _I, _I, _P, C.c_float, _P, _P]),
+    ("d3f_ind_max_pool", _I, [_P, _P, _I, _I, _I, _I, _P, _P, _Z, _P, _P, _P]),
+    ("d3f_closest_pool", _I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    ("d3f_l2_normalize", _I, [_P, _I, _I, _F, _P, _P, _P]),
+    ("d3f_unary_pair_forward", _I, [_P, _I, _P, _I, _P, _I, _I, _P, C.c_float, _P, _P, _P]),
     ("d3f_detection_scores_workspace_bytes", _Z, [_I, _I]),
-    ("d3f_detection_scores", _I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P]),
-    ("d3f_affine_leaky", _I, [_P, _I, _I, _P, _P, _P, _F, _P, _P]),
+    ("d3f_detection_scores", _I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _Z, _P, _P]),
+    ("d3f_affine_leaky", _I, [_P, _I, _I, _P, _P, _P, _F, _P, _P, _P]),
 ]
 
 _lib = None

@@ -64,8 +64,9 @@ def _epilogue_args(epilogue):
     return scale, shift, (-1.0 if alpha is None else float(alpha))
 
 
-def unary_convolution(features, K_values, *, epilogue=None, residual=None):
-    """features[N,Cin] @ K_values[Cin,Cout] (tf.matmul, :90-99)."""
+def unary_convolution(features, K_values, *, epilogue=None, residual=None, rows=None):
+    """features[N,Cin] @ K_values[Cin,Cout] (tf.matmul, :90-99).
+    rows (extension): int32 device scalar holding the actual row count when `features` is a capacity-sized buffer."""
     x = features.contiguous()
     w = K_values.contiguous()
     N, Cin = x.shape
@@ -76,14 +77,14 @@ def unary_convolution(features, K_values, *, epilogue=None, residual=None):
     out = torch.empty((N, Cout), dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().d3f_unary_forward(_lib.ptr(x), _lib.ptr(w), _lib.ptr(packed_weight(w)), N, Cin, Cout, _lib.ptr(scale), _lib.ptr(shift),
                                             None, _lib.ptr(residual.contiguous()) if residual is not None else None,
-                                            alpha, _lib.ptr(out), _lib.stream()), "d3f_unary_forward")
+                                            alpha, _lib.ptr(out), _lib.stream(), _lib.ptr(rows)), "d3f_unary_forward")
     return out
 
 
 _pair_cache = {}       # (id(w1), id(w2)) -> (refs, versions, packed image of the folded [w1*s1 ; w2*s2], shift1 + shift2)
 
 
-def unary_pair_convolution(x1, w1, affine1, x2, w2, affine2, alpha):
+def unary_pair_convolution(x1, w1, affine1, x2, w2, affine2, alpha, *, rows=None):
     """leaky((x1 @ w1) * s1 + t1 + (x2 @ w2) * s2 + t2) as ONE GEMM over the concatenated K -- the conv3 + shortcut
     + add + LeakyReLU tail of a resnetb block (models/network_blocks.py:343-368). affine = (scale, shift) of the
     unary's inference batch norm. The scales are folded into the weights once per weight pair (float64), so neither
@@ -98,8 +99,8 @@ def unary_pair_convolution(x1, w1, affine1, x2, w2, affine2, alpha):
         raise ValueError("unary_pair_convolution: shapes %s@%s + %s@%s" % (tuple(x1.shape), tuple(w1.shape),
                                                                              tuple(x2.shape), tuple(w2.shape)))
     if not USE_TENSOR_CORES or C1 % 32 != 0 or C2 % 4 != 0:
-        shortcut = unary_convolution(x2, w2, epilogue=(s2, t2, None))
-        return unary_convolution(x1, w1, epilogue=(s1, t1, alpha), residual=shortcut)
+        shortcut = unary_convolution(x2, w2, epilogue=(s2, t2, None), rows=rows)
+        return unary_convolution(x1, w1, epilogue=(s1, t1, alpha), residual=shortcut, rows=rows)
     key = (id(w1), id(w2))
     hit = _pair_cache.get(key)
     vers = (w1._version, w2._version, s1._version, s2._version, t1._version, t2._version)
@@ -117,7 +118,7 @@ def unary_pair_convolution(x1, w1, affine1, x2, w2, affine2, alpha):
     out = torch.empty((N, Cout), dtype=torch.float32, device=x1.device)
     _lib.check(_lib.lib().d3f_unary_pair_forward(_lib.ptr(x1), C1, _lib.ptr(x2), C2, _lib.ptr(hit[2]), N, Cout,
                                                  _lib.ptr(hit[3]), -1.0 if alpha is None else float(alpha),
-                                                 _lib.ptr(out), _lib.stream()), "d3f_unary_pair_forward")
+                                                 _lib.ptr(out), _lib.stream(), _lib.ptr(rows)), "d3f_unary_pair_forward")
     return out
 
 
@@ -129,10 +130,13 @@ def _check_enums(KP_influence, aggregation_mode):
 
 
 def KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
-               KP_influence, aggregation_mode, *, epilogue=None, bias=None, query_order=None):
+               KP_influence, aggregation_mode, *, epilogue=None, bias=None, query_order=None, rows_q=None,
+               rows_s=None):
     """Rigid KPConv (:161-255): one fused launch sequence, no [N,H,K,*] intermediates.
     query_order (extension): int32[Nq] visiting order of the queries (hash-grid cell order from the pyramid);
-    a pure scheduling hint -- every query still writes its own output row."""
+    a pure scheduling hint -- every query still writes its own output row.
+    rows_q / rows_s (extension): int32 device scalars with the actual query / support counts when the tensors are
+    capacity-sized buffers (the shadow index is then the actual support count)."""
     _check_enums(KP_influence, aggregation_mode)
     q, s = query_points.contiguous(), support_points.contiguous()
     idx, f = neighbors_indices.contiguous(), features.contiguous()
@@ -149,13 +153,15 @@ def KPConv_ops(query_points, support_points, neighbors_indices, features, K_poin
     _lib.check(L.d3f_kpconv_forward(_lib.ptr(q), _lib.ptr(s), _lib.ptr(idx), _lib.ptr(f), _lib.ptr(Kp), _lib.ptr(W),
                                     _lib.ptr(packed_weight(W)), _lib.ptr(query_order), Nq, Ns, H, K, Cin, Cout, float(KP_extent), _INFLUENCE[KP_influence],
                                     _MODE[aggregation_mode], 1, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(bias),
-                                    alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream()),
+                                    alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(), _lib.stream(), _lib.ptr(rows_q),
+                                    _lib.ptr(rows_s)),
                "d3f_kpconv_forward")
     return out
 
 
 def KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets, modulations,
-                      K_values, KP_extent, KP_influence, mode, *, epilogue=None, query_order=None):
+                      K_values, KP_extent, KP_influence, mode, *, epilogue=None, query_order=None, rows_q=None,
+                      rows_s=None):
     """Deformable second stage (:379-499)."""
     _check_enums(KP_influence, mode)
     q, s = query_points.contiguous(), support_points.contiguous()
@@ -172,7 +178,8 @@ def KPConv_deform_ops(query_points, support_points, neighbors_indices, features,
                                            _lib.ptr(off), _lib.ptr(mod), _lib.ptr(W), _lib.ptr(packed_weight(W)), _lib.ptr(query_order), Nq, Ns, H, K, Cin, Cout,
                                            float(KP_extent), _INFLUENCE[KP_influence], _MODE[mode], _lib.ptr(scale),
                                            _lib.ptr(shift), None, alpha, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                           _lib.stream()), "d3f_kpconv_deform_forward")
+                                           _lib.stream(), _lib.ptr(rows_q), _lib.ptr(rows_s)),
+               "d3f_kpconv_deform_forward")
     return out
 
 
@@ -193,18 +200,20 @@ def _kernel_points(K_radius, num_kpoints, device, fixed):
 
 
 def KPConv(query_points, support_points, neighbors_indices, features, K_values, fixed="center", KP_extent=1.0,
-           KP_influence="linear", aggregation_mode="sum", *, epilogue=None, query_order=None):
+           KP_influence="linear", aggregation_mode="sum", *, epilogue=None, query_order=None, rows_q=None,
+           rows_s=None):
     """:102-158 -- kernel-point disposition of radius 1.5*KP_extent, then KPConv_ops."""
     K_radius = 1.5 * KP_extent
     num_kpoints = int(K_values.shape[0])
     K_points = _kernel_points(K_radius, num_kpoints, query_points.device, fixed)
     return KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values, KP_extent,
-                      KP_influence, aggregation_mode, epilogue=epilogue, query_order=query_order)
+                      KP_influence, aggregation_mode, epilogue=epilogue, query_order=query_order, rows_q=rows_q,
+                      rows_s=rows_s)
 
 
 def KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values, fixed="center",
                       KP_extent=1.0, KP_influence="linear", aggregation_mode="sum", modulated=False, *,
-                      epilogue=None, query_order=None):
+                      epilogue=None, query_order=None, rows_q=None, rows_s=None):
     """:258-376 -- rigid KPConv producing 3K (4K if modulated) offsets (+ bias), then the deformed conv."""
     K_radius = 1.5 * KP_extent
     num_kpoints = int(K_values.shape[0])
@@ -219,7 +228,8 @@ def KPConv_deformable(query_points, support_points, neighbors_indices, features,
         K_values0 = torch.zeros((num_kpoints, K_values.shape[1], offset_dim), device=query_points.device)
         b0 = torch.zeros((offset_dim,), device=query_points.device)
     features0 = KPConv_ops(query_points, support_points, neighbors_indices, features, K_points, K_values0, KP_extent,
-                           KP_influence, aggregation_mode, bias=b0, query_order=query_order)
+                           KP_influence, aggregation_mode, bias=b0, query_order=query_order, rows_q=rows_q,
+                           rows_s=rows_s)
     if modulated:
         offsets = features0[:, :points_dim * num_kpoints].reshape(-1, num_kpoints, points_dim)
         modulations = 2 * torch.sigmoid(features0[:, points_dim * num_kpoints:])
@@ -229,4 +239,4 @@ def KPConv_deformable(query_points, support_points, neighbors_indices, features,
     offsets = offsets * KP_extent
     return KPConv_deform_ops(query_points, support_points, neighbors_indices, features, K_points, offsets,
                              modulations, K_values, KP_extent, KP_influence, aggregation_mode, epilogue=epilogue,
-                             query_order=query_order)
+                             query_order=query_order, rows_q=rows_q, rows_s=rows_s)

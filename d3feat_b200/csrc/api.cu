@@ -107,13 +107,15 @@ size_t d3f_pyramid_workspace_bytes(int B, const d3f_pyramid_spec* spec, const in
 int d3f_pyramid_build(const float* points, const int* lengths, int B, int N0, const d3f_pyramid_spec* spec,
                       const float* host_bbox, float* const* out_points, int* const* out_lengths,
                       int* const* out_neighbors, int* const* out_pools, int* const* out_upsamples, const int* capacity,
-                      int* out_level_sizes, void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
+                      int* out_level_sizes, void* workspace, size_t workspace_bytes, d3f_stream_t stream,
+                      int* d_counts, int* d_status, const int* n0_dev) {
   D3F_REQUIRE((points != nullptr || N0 == 0) && lengths != nullptr && out_points && out_lengths && out_neighbors &&
                   out_pools && out_upsamples && workspace,
               D3F_ERR_INVALID, "d3f_pyramid_build: null pointer");
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "d3f_pyramid_build: B=%d", B);
   return pyramid_build(points, lengths, B, N0, spec, host_bbox, out_points, out_lengths, out_neighbors, out_pools,
-                       out_upsamples, capacity, out_level_sizes, workspace, workspace_bytes, (cudaStream_t)stream);
+                       out_upsamples, capacity, out_level_sizes, workspace, workspace_bytes, (cudaStream_t)stream,
+                       d_counts, d_status, n0_dev);
 }
 
 size_t d3f_packed_weight_floats(int K, int N) { return tc_packed_floats(K, N); }
@@ -125,30 +127,32 @@ int d3f_pack_weight(const float* W, int K, int N, float* packed, d3f_stream_t st
 int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const float* feat, const float* Kp,
                        const float* W, const float* W_packed, const int* query_order, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent, int influence,
                        int mode, int normalize, const float* bn_scale, const float* bn_shift, const float* bias,
-                       float leaky_alpha, float* out, void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
+                       float leaky_alpha, float* out, void* workspace, size_t workspace_bytes, d3f_stream_t stream,
+                       const int* nq_dev, const int* ns_dev) {
   D3F_REQUIRE(Nq == 0 || (q && s && idx && feat && Kp && W && out && workspace), D3F_ERR_INVALID,
               "d3f_kpconv_forward: null pointer");
   return kpconv_forward_impl(false, q, s, idx, feat, Kp, nullptr, nullptr, W, W_packed, query_order, Nq, Ns, H, K, Cin, Cout, extent,
                              influence, mode, normalize, bn_scale, bn_shift, bias, leaky_alpha, out, workspace,
-                             workspace_bytes, (cudaStream_t)stream);
+                             workspace_bytes, (cudaStream_t)stream, nq_dev, ns_dev);
 }
 
 int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, const float* feat, const float* Kp,
                               const float* offsets, const float* modulations, const float* W, const float* W_packed,
                               const int* query_order, int Nq, int Ns, int H, int K, int Cin, int Cout, float extent, int influence, int mode, const float* bn_scale,
                               const float* bn_shift, const float* bias, float leaky_alpha, float* out,
-                              void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
+                              void* workspace, size_t workspace_bytes, d3f_stream_t stream, const int* nq_dev,
+                              const int* ns_dev) {
   D3F_REQUIRE(Nq == 0 || (q && s && idx && feat && Kp && W && out && workspace && offsets), D3F_ERR_INVALID,
               "d3f_kpconv_deform_forward: null pointer");
   return kpconv_forward_impl(true, q, s, idx, feat, Kp, offsets, modulations, W, W_packed, query_order, Nq, Ns, H, K, Cin, Cout, extent,
                              influence, mode, 0, bn_scale, bn_shift, bias, leaky_alpha, out, workspace,
-                             workspace_bytes, (cudaStream_t)stream);
+                             workspace_bytes, (cudaStream_t)stream, nq_dev, ns_dev);
 }
 
 int d3f_unary_forward(const float* x, const float* W, const float* W_packed, int N, int Cin, int Cout,
                       const float* bn_scale,
                       const float* bn_shift, const float* bias, const float* residual, float leaky_alpha, float* out,
-                      d3f_stream_t stream) {
+                      d3f_stream_t stream, const int* n_dev) {
   D3F_REQUIRE(N >= 0 && Cin >= 1 && Cout >= 1, D3F_ERR_INVALID, "d3f_unary_forward: bad shape N=%d Cin=%d Cout=%d", N,
               Cin, Cout);
   D3F_REQUIRE(N == 0 || (x && W && out), D3F_ERR_INVALID, "d3f_unary_forward: null pointer");
@@ -162,13 +166,15 @@ int d3f_unary_forward(const float* x, const float* W, const float* W_packed, int
   ep.residual = residual;
   ep.leaky_alpha = leaky_alpha;
   ep.row_map = nullptr;
+  ep.m_dev = n_dev;
   if (W_packed != nullptr && tc_gemm_supported(x, Cin))
     return tc_gemm(x, W_packed, out, N, Cout, Cin, ep, (cudaStream_t)stream);
   return gemm_f32(x, W, out, N, Cout, Cin, ep, (cudaStream_t)stream);
 }
 
 int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2, const float* W_packed, int N,
-                           int Cout, const float* shift, float leaky_alpha, float* out, d3f_stream_t stream) {
+                           int Cout, const float* shift, float leaky_alpha, float* out, d3f_stream_t stream,
+                           const int* n_dev) {
   D3F_REQUIRE(N >= 0 && Cin1 >= 1 && Cin2 >= 1 && Cout >= 1, D3F_ERR_INVALID,
               "d3f_unary_pair_forward: bad shape N=%d Cin=%d+%d Cout=%d", N, Cin1, Cin2, Cout);
   D3F_REQUIRE(N == 0 || (x1 && x2 && W_packed && out), D3F_ERR_INVALID, "d3f_unary_pair_forward: null pointer");
@@ -182,42 +188,44 @@ int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2,
   ep.residual = nullptr;
   ep.leaky_alpha = leaky_alpha;
   ep.row_map = nullptr;
+  ep.m_dev = n_dev;
   return tc_gemm(x1, W_packed, out, N, Cout, Cin1 + Cin2, ep, (cudaStream_t)stream, nullptr, x2, Cin1);
 }
 
 size_t d3f_ind_max_pool_workspace_bytes(int C) { return sizeof(unsigned) * ((size_t)(C > 0 ? C : 1) + 1); }
 
 int d3f_ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,
-                     size_t workspace_bytes, d3f_stream_t stream) {
+                     size_t workspace_bytes, d3f_stream_t stream, const int* n1_dev, const int* n2_dev) {
   D3F_REQUIRE(N2 == 0 || (x && inds && out && workspace), D3F_ERR_INVALID, "d3f_ind_max_pool: null pointer");
-  return ind_max_pool(x, inds, N1, N2, H, C, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  return ind_max_pool(x, inds, N1, N2, H, C, out, workspace, workspace_bytes, (cudaStream_t)stream, n1_dev, n2_dev);
 }
 
 int d3f_closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C, float* out,
-                     d3f_stream_t stream) {
+                     d3f_stream_t stream, const int* n1_dev, const int* n2_dev) {
   D3F_REQUIRE(N2 == 0 || (x && inds && out), D3F_ERR_INVALID, "d3f_closest_pool: null pointer");
-  return closest_pool(x, inds, N1, N2, ld_inds, C, out, (cudaStream_t)stream);
+  return closest_pool(x, inds, N1, N2, ld_inds, C, out, (cudaStream_t)stream, n1_dev, n2_dev);
 }
 
-int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream) {
+int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream, const int* n_dev) {
   D3F_REQUIRE(N == 0 || (x && out), D3F_ERR_INVALID, "d3f_l2_normalize: null pointer");
-  return l2_normalize(x, N, C, eps, out, (cudaStream_t)stream);
+  return l2_normalize(x, N, C, eps, out, (cudaStream_t)stream, n_dev);
 }
 
 size_t d3f_detection_scores_workspace_bytes(int N, int B) { return detection_scores_workspace_bytes(N, B); }
 
 int d3f_detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N, int H, int D,
-                         float* out_scores, void* workspace, size_t workspace_bytes, d3f_stream_t stream) {
+                         float* out_scores, void* workspace, size_t workspace_bytes, d3f_stream_t stream,
+                         const int* n_dev) {
   D3F_REQUIRE(N == 0 || (feats && neighbors && lengths && out_scores && workspace), D3F_ERR_INVALID,
               "d3f_detection_scores: null pointer");
   return detection_scores(feats, neighbors, lengths, B, N, H, D, out_scores, workspace, workspace_bytes,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, n_dev);
 }
 
 int d3f_affine_leaky(const float* x, int N, int C, const float* scale, const float* shift, const float* residual,
-                     float leaky_alpha, float* out, d3f_stream_t stream) {
+                     float leaky_alpha, float* out, d3f_stream_t stream, const int* n_dev) {
   D3F_REQUIRE(N == 0 || (x && out), D3F_ERR_INVALID, "d3f_affine_leaky: null pointer");
-  return affine_leaky(x, N, C, scale, shift, residual, leaky_alpha, out, (cudaStream_t)stream);
+  return affine_leaky(x, N, C, scale, shift, residual, leaky_alpha, out, (cudaStream_t)stream, n_dev);
 }
 
 }  // extern "C"

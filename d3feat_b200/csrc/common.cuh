@@ -66,6 +66,15 @@ __device__ __forceinline__ float ord2f(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
+// Row count of a launch: kernels are launched on a capacity-sized grid and read the actual number of rows from device
+// memory when the caller supplies it (the pyramid's level sizes are produced on the device; reading them back on the
+// host would put a synchronisation into every step). n_dev == nullptr: the capacity IS the row count.
+__device__ __forceinline__ int dyn_rows(int n_cap, const int* __restrict__ n_dev) {
+  if (n_dev == nullptr) return n_cap;
+  const int n = __ldg(n_dev);
+  return n < n_cap ? (n < 0 ? 0 : n) : n_cap;
+}
+
 // batch element of a stacked row index: largest b with start[b] <= i (start = exclusive scan of lengths)
 __device__ __forceinline__ int batch_of(const int* __restrict__ start, int B, int i) {
   int lo = 0, hi = B - 1;

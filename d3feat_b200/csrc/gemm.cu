@@ -10,8 +10,10 @@ namespace d3f {
 
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
-gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int Mcap, int N, int K,
                 Epilogue ep) {
+  const int M = ep.m_dev ? min(Mcap, max(__ldg(ep.m_dev) - ep.m_off, 0)) : Mcap;
+  if ((int)blockIdx.y * BM >= M) return;   // CTA-uniform: tiles beyond the actual row count
   constexpr int THREADS = (BM / TM) * (BN / TN);
   __shared__ float As[2][BK][BM + 4];
   __shared__ float Bs[2][BK][BN + 4];

@@ -50,9 +50,11 @@ int launch_batch_start(const int* len, int B, int* start, cudaStream_t stream) {
 }
 
 // bbox_ord[b*6 + {0,1,2}] = min (ordered uint), [3,4,5] = max. Must be pre-set to 0xFF.. / 0.
-__global__ void __launch_bounds__(256) bbox_batch_kernel(const float* __restrict__ pts, int N,
+__global__ void __launch_bounds__(256) bbox_batch_kernel(const float* __restrict__ pts, int Ncap,
+                                                         const int* __restrict__ n_dev,
                                                          const int* __restrict__ start, int B,
                                                          unsigned* __restrict__ bbox_ord) {
+  const int N = dyn_rows(Ncap, n_dev);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ceil_div(N, 32) * 32; i += gridDim.x * blockDim.x) {
     bool valid = i < N;
     int b = valid ? batch_of(start, B, i) : -1;
@@ -100,7 +102,7 @@ int bbox_device(const float* pts, int N, float* out_bbox, cudaStream_t stream) {
   D3F_CUDA(cudaMemsetAsync(ord + 3, 0, 3 * sizeof(unsigned), stream));
   if (N > 0) {
     int blocks = min(ceil_div(N, 256), kNumSMs * 4);
-    bbox_batch_kernel<<<blocks, 256, 0, stream>>>(pts, N, nullptr, 1, ord);
+    bbox_batch_kernel<<<blocks, 256, 0, stream>>>(pts, N, nullptr, nullptr, 1, ord);
     D3F_LAUNCH_CHECK("bbox_batch_kernel");
   }
   bbox_decode_kernel<<<1, 32, 0, stream>>>(ord, out_bbox, 6);
@@ -131,9 +133,10 @@ __device__ __forceinline__ CloudGrid cloud_grid(const unsigned* __restrict__ bbo
 // sort key = cloud << (cell_bits+1) | folded reference key. err[0] is raised if a key needs more than
 // cell_bits bits (host bbox too small).
 __global__ void __launch_bounds__(256)
-cell_key_kernel(const float* __restrict__ pts, int N, const int* __restrict__ start, int B,
-                const unsigned* __restrict__ bbox_ord, float dl, int cell_bits, uint64_t* __restrict__ keys,
+cell_key_kernel(const float* __restrict__ pts, int Ncap, const int* __restrict__ n_dev, const int* __restrict__ start,
+                int B, const unsigned* __restrict__ bbox_ord, float dl, int cell_bits, uint64_t* __restrict__ keys,
                 uint32_t* __restrict__ vals, int* __restrict__ err) {
+  const int N = dyn_rows(Ncap, n_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   int b = batch_of(start, B, i);
@@ -156,8 +159,9 @@ cell_key_kernel(const float* __restrict__ pts, int N, const int* __restrict__ st
   vals[i] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(256) segment_head_kernel(const uint64_t* __restrict__ keys, int N,
-                                                           int* __restrict__ flags) {
+__global__ void __launch_bounds__(256) segment_head_kernel(const uint64_t* __restrict__ keys, int Ncap,
+                                                           const int* __restrict__ n_dev, int* __restrict__ flags) {
+  const int N = dyn_rows(Ncap, n_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N) flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1 : 0;
 }
@@ -166,13 +170,16 @@ __global__ void __launch_bounds__(256) segment_head_kernel(const uint64_t* __res
 __global__ void __launch_bounds__(128)
 cell_reduce_kernel(const float* __restrict__ pts, const uint64_t* __restrict__ keys,
                    const uint32_t* __restrict__ vals, const int* __restrict__ flags,
-                   const int* __restrict__ cell_of, int N, int cell_bits, const int* __restrict__ classes,
-                   int ldim, float* __restrict__ out_pts, int* __restrict__ out_classes,
-                   int* __restrict__ out_batch_len, int* __restrict__ cell_first, int* __restrict__ cell_count) {
+                   const int* __restrict__ cell_of, int Ncap, const int* __restrict__ n_dev, int out_cap, int cell_bits,
+                   const int* __restrict__ classes, int ldim, float* __restrict__ out_pts,
+                   int* __restrict__ out_classes, int* __restrict__ out_batch_len, int* __restrict__ cell_first,
+                   int* __restrict__ cell_count) {
+  const int N = dyn_rows(Ncap, n_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N || !flags[i]) return;
   uint64_t key = keys[i];
   int m = cell_of[i];
+  if (m >= out_cap) return;   // more cells than the caller's output capacity: reported through out_M (status kernel)
   float sx = 0.f, sy = 0.f, sz = 0.f;
   int count = 0;
   int j = i;
@@ -213,9 +220,18 @@ cell_feature_kernel(const float* __restrict__ feats, int fdim, const uint32_t* _
   out_feats[(size_t)m * fdim + c] = __fdiv_rn(s, (float)count);
 }
 
-// a sort-key overflow (points outside the host bbox) is reported to the caller as out_M = -1
-__global__ void subsample_status_kernel(const int* __restrict__ err, int* __restrict__ out_M) {
-  if (*err) *out_M = -1;
+// a sort-key overflow (points outside the host bbox) is reported to the caller as out_M = -1, more cells than the
+// output capacity as out_M = -2; `status` (optional) accumulates the same conditions as bits 1 / 2 for callers that
+// never read out_M on the host (the graph-replayed pyramid)
+__global__ void subsample_status_kernel(const int* __restrict__ err, int* __restrict__ out_M, int out_cap,
+                                        int* __restrict__ status) {
+  if (*err) {
+    *out_M = -1;
+    if (status) atomicOr(status, 1);
+  } else if (*out_M > out_cap) {
+    *out_M = -2;
+    if (status) atomicOr(status, 2);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -270,7 +286,8 @@ size_t grid_subsample_workspace_bytes(int N, int B) {
 int grid_subsample(const float* pts, const int* batch_len, int B, int N, float dl, const float* feats, int fdim,
                    const int* classes, int ldim, const float* host_bbox, float* out_pts, float* out_feats,
                    int* out_classes, int* out_batch_len, int* out_M, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const int* n_dev, int out_capacity, int* status) {
+  if (out_capacity < 0) out_capacity = N;   // a subsampled cloud never has more points than its parent
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "grid_subsample: B=%d must be in [1,%d]", B, kMaxBatch);
   D3F_REQUIRE(N >= 0 && dl > 0.f, D3F_ERR_INVALID, "grid_subsample: N=%d, dl=%g invalid", N, (double)dl);
   D3F_REQUIRE(host_bbox != nullptr, D3F_ERR_INVALID, "grid_subsample: host_bbox is required");
@@ -301,20 +318,21 @@ int grid_subsample(const float* pts, const int* batch_len, int B, int N, float d
     D3F_CUDA(cudaMemset2DAsync(w.bbox_ord, 6 * sizeof(unsigned), 0xff, 3 * sizeof(unsigned), B, stream));
   }
   int blocks = min(ceil_div(N, 256), kNumSMs * 8);
-  bbox_batch_kernel<<<blocks, 256, 0, stream>>>(pts, N, w.start, B, w.bbox_ord);
+  bbox_batch_kernel<<<blocks, 256, 0, stream>>>(pts, N, n_dev, w.start, B, w.bbox_ord);
   D3F_LAUNCH_CHECK("bbox_batch_kernel");
-  cell_key_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(pts, N, w.start, B, w.bbox_ord, dl, cell_bits,
+  cell_key_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(pts, N, n_dev, w.start, B, w.bbox_ord, dl, cell_bits,
                                                         w.sort.keys[0], w.sort.vals[0], w.err);
   D3F_LAUNCH_CHECK("cell_key_kernel");
-  int cur = radix_sort_pairs(w.sort, N, cell_bits + 1 + bbits, stream);
+  int cur = radix_sort_pairs(w.sort, N, cell_bits + 1 + bbits, stream, n_dev);
   if (cur < 0) return cur;
-  segment_head_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(w.sort.keys[cur], N, w.flags);
+  segment_head_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(w.sort.keys[cur], N, n_dev, w.flags);
   D3F_LAUNCH_CHECK("segment_head_kernel");
-  int rc = exclusive_scan_i32(w.flags, w.cell_of, N, out_M, w.scan_scratch, stream);
+  int rc = exclusive_scan_i32(w.flags, w.cell_of, N, out_M, w.scan_scratch, stream, n_dev);
   if (rc) return rc;
   cell_reduce_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(pts, w.sort.keys[cur], w.sort.vals[cur], w.flags,
-                                                           w.cell_of, N, cell_bits, classes, ldim, out_pts,
-                                                           out_classes, out_batch_len, w.cell_first, w.cell_count);
+                                                           w.cell_of, N, n_dev, out_capacity, cell_bits, classes,
+                                                           ldim, out_pts, out_classes, out_batch_len, w.cell_first,
+                                                           w.cell_count);
   D3F_LAUNCH_CHECK("cell_reduce_kernel");
   if (fdim > 0) {
     long long work = (long long)N * fdim;  // upper bound on M * fdim
@@ -323,7 +341,7 @@ int grid_subsample(const float* pts, const int* batch_len, int B, int N, float d
                                                                             out_feats);
     D3F_LAUNCH_CHECK("cell_feature_kernel");
   }
-  subsample_status_kernel<<<1, 1, 0, stream>>>(w.err, out_M);
+  subsample_status_kernel<<<1, 1, 0, stream>>>(w.err, out_M, out_capacity, status);
   D3F_LAUNCH_CHECK("subsample_status_kernel");
   return D3F_OK;
 }

@@ -36,14 +36,17 @@ struct Stage1Params {
   float shadow;               // coordinate of the shadow support point (1e6 / 1000)
   float* wf;                  // [n1-n0, K*Cin]
   float* inv_nn;              // [n1-n0] or null
+  const int* nq_dev;          // optional: actual query / support counts in device memory (Nq / Ns are capacities)
+  const int* ns_dev;
 };
 
 // One warp per support point: pack (x, y, z, flag) so that phase A needs ONE 16-byte load per neighbour instead of
 // three scattered 4-byte loads plus a flag byte; entry Ns is the shadow point. mode 0: flag = 0, 1: flag = (row sum
 // of the features > 0) (:250-251), 2: flag slot carries the scalar feature itself (Cin = 1 kernel).
 __global__ void __launch_bounds__(256) prep_supports_kernel(const float* __restrict__ s, const float* __restrict__ feat,
-                                                            int Ns, int Cin, int mode, float shadow,
-                                                            float4* __restrict__ s4) {
+                                                            int Ns_cap, const int* __restrict__ ns_dev, int Cin,
+                                                            int mode, float shadow, float4* __restrict__ s4) {
+  const int Ns = dyn_rows(Ns_cap, ns_dev);
   int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp > Ns) return;
   if (warp == Ns) {
@@ -67,8 +70,10 @@ __global__ void __launch_bounds__(256) prep_supports_kernel(const float* __restr
 // float4, so a warp packs 32 / G supports per pass instead of one.
 template <int G>
 __global__ void __launch_bounds__(256) prep_supports_vec_kernel(const float* __restrict__ s,
-                                                                const float* __restrict__ feat, int Ns, int Cin,
+                                                                const float* __restrict__ feat, int Ns_cap,
+                                                                const int* __restrict__ ns_dev, int Cin,
                                                                 float shadow, float4* __restrict__ s4) {
+  const int Ns = dyn_rows(Ns_cap, ns_dev);
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = t / G, gl = t % G;
   float sum = 0.f;
@@ -91,12 +96,13 @@ __global__ void __launch_bounds__(256) prep_supports_vec_kernel(const float* __r
 
 template <int K, int VEC, bool DEFORM>
 __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Params p) {
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
   static_assert(K <= kKMax, "K too large");
   __shared__ __align__(16) float wts[kS1Warps][32 * kWStride];
   __shared__ float kp_s[kS1Warps][kKMax * 3];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = p.n0 + blockIdx.x * kS1Warps + warp;
-  if (n >= p.n1) return;  // warp-uniform
+  if (n >= n1_) return;  // warp-uniform
   const int qid = p.order ? p.order[n] : n;
 
   // kernel points of this query (rigid: shared by all queries; deformable: Kp + offsets[n])
@@ -125,9 +131,9 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_kernel(Stage1Para
     for (int h0 = 0; h0 < p.H; h0 += 32) {
       // ---- phase A: lane <-> neighbour h0+lane: correlation weights to the K kernel points ------------
       const int h = h0 + lane;
-      int id = (h < p.H) ? row[h] : p.Ns;
-      if (id < 0 || id > p.Ns) id = p.Ns;  // -1 padding of the non-batch op behaves like the shadow
-      const bool real = id < p.Ns;
+      int id = (h < p.H) ? row[h] : Ns_;
+      if (id < 0 || id > Ns_) id = Ns_;  // -1 padding of the non-batch op behaves like the shadow
+      const bool real = id < Ns_;
       const float4 sp = __ldg(&p.s4[id]);   // entry Ns = shadow point
       const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
       float w[kKMax];
@@ -253,6 +259,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 
 template <int CPL, int QPW, bool DEFORM>
 __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : 6) kpconv_stage1_v2_kernel(Stage1Params p) {
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
   constexpr int K = 15, KP = 16;
   constexpr int LPQ = 32 / QPW;  // lanes (= neighbour slots per pass) per query
   static_assert(CPL == 2 || CPL == 4, "channels per lane");
@@ -261,9 +268,9 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : 6) kpconv_stage1
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane / LPQ, sl = lane % LPQ;
   const int nfirst = p.n0 + (blockIdx.x * kS1Warps + warp) * QPW;
-  if (nfirst >= p.n1) return;  // warp-uniform
+  if (nfirst >= n1_) return;  // warp-uniform
   const int n = nfirst + sub;
-  const bool qvalid = n < p.n1;
+  const bool qvalid = n < n1_;
   const int nslot = qvalid ? n : nfirst;  // invalid half-warps shadow the first query (results discarded)
   const int nq = p.order ? p.order[nslot] : nslot;
 
@@ -293,9 +300,9 @@ __global__ void __launch_bounds__(kS1Warps * 32, CPL == 4 ? 4 : 6) kpconv_stage1
     for (int h0 = 0; h0 < p.H; h0 += LPQ) {
       // ---- phase A: lane <-> neighbour h0+sl of this lane's query ---------------------------------------
       const int h = h0 + sl;
-      int id = (h < p.H) ? row[h] : p.Ns;
-      if (id < 0 || id > p.Ns) id = p.Ns;
-      const bool real = id < p.Ns;
+      int id = (h < p.H) ? row[h] : Ns_;
+      if (id < 0 || id > Ns_) id = Ns_;
+      const bool real = id < Ns_;
       const float4 sp = __ldg(&p.s4[id]);   // entry Ns = shadow point
       const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
       float w[KP];
@@ -415,12 +422,13 @@ __device__ __forceinline__ void split3(float x, unsigned& hi, unsigned& lo) {
 // generic instantiation keeps the runtime switches for constant / gaussian / closest.
 template <int NT, bool DEFORM, bool FAST>
 __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1Params p) {
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
   constexpr int K = 15;
   static_assert(NT % 4 == 0, "one float4 per four n-tiles");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int n = p.n0 + blockIdx.x * kS1Warps + warp;
-  if (n >= p.n1) return;  // warp-uniform
+  if (n >= n1_) return;  // warp-uniform
   const int qid = p.order ? p.order[n] : n;
   // this lane's two kernel points (rigid: shared by all queries; deformable: Kp + offsets[query])
   const int kA = g, kB = g + 8;
@@ -453,11 +461,11 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1
 
     for (int h0 = 0; h0 < p.H; h0 += 8) {
       const int ha = h0 + t, hb = h0 + t + 4;
-      int ida = ha < p.H ? row[ha] : p.Ns, idb = hb < p.H ? row[hb] : p.Ns;
-      if (ida < 0 || ida > p.Ns) ida = p.Ns;
-      if (idb < 0 || idb > p.Ns) idb = p.Ns;
+      int ida = ha < p.H ? row[ha] : Ns_, idb = hb < p.H ? row[hb] : Ns_;
+      if (ida < 0 || ida > Ns_) ida = Ns_;
+      if (idb < 0 || idb > Ns_) idb = Ns_;
       const float4 spa = __ldg(&p.s4[ida]), spb = __ldg(&p.s4[idb]);
-      const bool reala = ida < p.Ns, realb = idb < p.Ns;
+      const bool reala = ida < Ns_, realb = idb < Ns_;
       // feature rows in fragment layout (issued before the weight math: latency overlaps it). A register-
       // pipelined variant (rows one step ahead) was measured SLOWER: occupancy (63 vs 93 regs) matters more.
       float fa[NT], fb[NT];
@@ -554,12 +562,13 @@ constexpr int kAnyKMax = 64;
 
 template <bool DEFORM>
 __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_anyk_kernel(Stage1Params p, int K) {
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
   extern __shared__ float anyk_smem[];   // per warp: wts[K][32], kp[K][3]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* wts = anyk_smem + (size_t)warp * (K * 32 + K * 3);
   float* kp_s = wts + K * 32;
   const int n = p.n0 + blockIdx.x * kS1Warps + warp;
-  if (n >= p.n1) return;  // warp-uniform
+  if (n >= n1_) return;  // warp-uniform
   const int qid = p.order ? p.order[n] : n;
   for (int t = lane; t < K * 3; t += 32) {
     float v = p.Kp[t];
@@ -574,9 +583,9 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_anyk_kernel(Stage
   int nn_count = 0;
   for (int h0 = 0; h0 < p.H || h0 == 0; h0 += 32) {
     const int h = h0 + lane;
-    int id = (h < p.H) ? row[h] : p.Ns;
-    if (id < 0 || id > p.Ns) id = p.Ns;
-    const bool real = id < p.Ns;
+    int id = (h < p.H) ? row[h] : Ns_;
+    if (id < 0 || id > Ns_) id = Ns_;
+    const bool real = id < Ns_;
     const float4 sp = __ldg(&p.s4[id]);
     const float rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
     float dmin = 3.0e38f;
@@ -676,12 +685,14 @@ struct Cin1Params {
   float leaky_alpha;
   const int* order;
   float* out;
+  const int* nq_dev; const int* ns_dev;
 };
 
 // 8 lanes per query (4 queries per warp): a lane walks neighbours sl, sl+8, ... and keeps the 15 partial sums
 // wf[k] in registers; a 3-step shuffle reduction inside the 8-lane group finishes wf, then the group's lanes split the
 // output channels with W[15, Cout] staged once per CTA in shared memory.
 __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), Nq_ = dyn_rows(p.Nq, p.nq_dev);
   constexpr int K = 15;
   extern __shared__ float c1_smem[];   // W[K*Cout] then Kp[K*3]
   float* Ws = c1_smem;
@@ -692,9 +703,9 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
   const int lane = threadIdx.x & 31;
   const int sub = lane >> 3, sl = lane & 7;
   const int slot0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
-  if (slot0 >= p.Nq) return;  // warp-uniform
+  if (slot0 >= Nq_) return;  // warp-uniform
   const int slot = slot0 + sub;
-  const bool qvalid = slot < p.Nq;
+  const bool qvalid = slot < Nq_;
   const int n = p.order ? p.order[qvalid ? slot : slot0] : (qvalid ? slot : slot0);
   const float qx = p.q[3 * (size_t)n], qy = p.q[3 * (size_t)n + 1], qz = p.q[3 * (size_t)n + 2];
   const int* row = p.idx + (size_t)n * p.H;
@@ -704,7 +715,7 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
   int nn = 0;
   for (int h = sl; h < p.H; h += 8) {
     int id = row[h];
-    if (id < 0 || id > p.Ns) id = p.Ns;
+    if (id < 0 || id > Ns_) id = Ns_;
     const float4 sp = __ldg(&p.s4[id]);   // (x, y, z, feature); entry Ns = shadow point with feature 0
     const float f = sp.w, rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
     nn += f > 0.f ? 1 : 0;
@@ -803,6 +814,7 @@ size_t kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout) {
   b += 2 * align_up((size_t)chunk * sizeof(float), 256);
   b += align_up((size_t)(Ns + 1) * sizeof(float4), 256);
   b += align_up(tc_gemm_split_ws_floats(chunk, Cout, K * Cin) * sizeof(float), 256);
+  b += align_up(kpconv_fused_workspace_bytes(), 256);
   return b + 1024;
 }
 
@@ -812,7 +824,8 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
                         float extent,
                         int influence, int mode, int normalize,
                         const float* bn_scale, const float* bn_shift, const float* bias, float leaky_alpha,
-                        float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                        float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                        const int* nq_dev, const int* ns_dev) {
   D3F_REQUIRE(Nq >= 0 && Ns >= 0 && H >= 0 && Cin >= 1 && Cout >= 1, D3F_ERR_INVALID,
               "kpconv: bad shape Nq=%d Ns=%d H=%d Cin=%d Cout=%d", Nq, Ns, H, Cin, Cout);
   D3F_REQUIRE(K >= 1 && K <= kAnyKMax, D3F_ERR_INVALID, "kpconv: num_kernel_points=%d outside [1, %d]", K, kAnyKMax);
@@ -841,13 +854,13 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     const float shadow = deform ? 1000.f : 1e6f;
     const bool vec = pmode == 1 && Cin % 4 == 0 && Cin >= 32 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0;
     if (vec && Cin < 64)
-      prep_supports_vec_kernel<8><<<ceil_div((Ns + 1) * 8, 256), 256, 0, stream>>>(s, feat, Ns, Cin, shadow, s4);
+      prep_supports_vec_kernel<8><<<ceil_div((Ns + 1) * 8, 256), 256, 0, stream>>>(s, feat, Ns, ns_dev, Cin, shadow, s4);
     else if (vec && Cin < 128)
-      prep_supports_vec_kernel<16><<<ceil_div((Ns + 1) * 16, 256), 256, 0, stream>>>(s, feat, Ns, Cin, shadow, s4);
+      prep_supports_vec_kernel<16><<<ceil_div((Ns + 1) * 16, 256), 256, 0, stream>>>(s, feat, Ns, ns_dev, Cin, shadow, s4);
     else if (vec)
-      prep_supports_vec_kernel<32><<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, shadow, s4);
+      prep_supports_vec_kernel<32><<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, ns_dev, Cin, shadow, s4);
     else
-      prep_supports_kernel<<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, Cin, pmode, shadow, s4);
+      prep_supports_kernel<<<ceil_div((Ns + 1) * 32, 256), 256, 0, stream>>>(s, feat, Ns, ns_dev, Cin, pmode, shadow, s4);
     D3F_LAUNCH_CHECK("prep_supports_kernel");
   }
   if (Cin == 1 && !deform && K == 15) {
@@ -862,11 +875,18 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     c1.bn_scale = bn_scale; c1.bn_shift = bn_shift; c1.bias = bias; c1.leaky_alpha = leaky_alpha;
     c1.order = query_order;
     c1.out = out;
+    c1.nq_dev = nq_dev; c1.ns_dev = ns_dev;
     const size_t c1_smem = (size_t)(K * Cout + K * 3) * sizeof(float);
     D3F_REQUIRE(c1_smem <= 48 * 1024, D3F_ERR_CAPACITY, "kpconv (Cin = 1): Cout=%d too wide for the first-layer kernel", Cout);
     kpconv_cin1_kernel<<<ceil_div(ceil_div(Nq, 4) * 32, 256), 256, c1_smem, stream>>>(c1);
     D3F_LAUNCH_CHECK("kpconv_cin1_kernel");
     return D3F_OK;
+  }
+  if (!deform && W_packed != nullptr &&
+      kpconv_fused_supported(Nq, H, K, Cin, Cout, influence, mode, feat, W, out, query_order)) {
+    float* w_img = cv.take<float>(kpconv_fused_workspace_bytes() / sizeof(float));
+    return kpconv_fused_forward(q, s4, idx, feat, Kp, W, w_img, Nq, Ns, H, Cout, extent, norm ? 1 : 0, bn_scale, bn_shift,
+                                bias, leaky_alpha, out, stream, nq_dev, ns_dev);
   }
   Stage1Params p;
   p.q = q; p.s4 = s4; p.idx = idx; p.feat = feat; p.count_nn = norm ? 1 : 0;
@@ -880,6 +900,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
   p.closest = mode == D3F_MODE_CLOSEST;
   p.shadow = deform ? 1000.f : 1e6f;
   p.order = query_order;
+  p.nq_dev = nq_dev; p.ns_dev = ns_dev;
   // Chunk pipeline: stage 1 of chunk i+1 (issue-bound on the SM pipes) runs on the caller's stream while the
   // contraction of chunk i (latency-bound, tensor pipe mostly idle, ~9 us of fixed cost per launch) runs on an
   // auxiliary stream; wf / inv_nn are double-buffered and the two streams are joined with events, so from the
@@ -909,6 +930,7 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     ep.leaky_alpha = leaky_alpha;
     // chunk rows are query SLOTS; with a visiting order the epilogue scatters row m to query order[n0 + m]
     ep.row_map = query_order ? query_order + n0 : nullptr;
+    ep.m_dev = nq_dev; ep.m_off = n0;                 // rows of this chunk that exist: clamp(*nq_dev - n0, 0, chunk)
     float* cbase = query_order ? out : out + (size_t)n0 * Cout;
     if (W_packed != nullptr && tc_gemm_supported(wf, K * Cin))
       rc = tc_gemm(wf, W_packed, cbase, p.n1 - n0, Cout, K * Cin, ep, gs, split_ws);   // chunk GEMMs are serial on gs

@@ -47,8 +47,10 @@ __device__ __forceinline__ int cell_coord(float v, float mn, float inv, int n) {
 // [cell_start[c], cell_start[c+1])), (3) scatter. The order of the points INSIDE a cell is whatever the atomics give;
 // no result depends on it (rows are emitted in (d2, index) order).
 __global__ void __launch_bounds__(256)
-cell_count_kernel(const float* __restrict__ s, int Ns, const int* __restrict__ start, int B, NbGrid g,
-                  uint32_t* __restrict__ cell_id, int* __restrict__ cell_cnt) {
+cell_count_kernel(const float* __restrict__ s, int Ns_cap, const int* __restrict__ ns_dev,
+                  const int* __restrict__ start, int B, NbGrid g, uint32_t* __restrict__ cell_id,
+                  int* __restrict__ cell_cnt) {
+  const int Ns = dyn_rows(Ns_cap, ns_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ns) return;
   int b = batch_of(start, B, i);
@@ -62,8 +64,10 @@ cell_count_kernel(const float* __restrict__ s, int Ns, const int* __restrict__ s
 
 // sorted_pts[pos] = (x, y, z, bits(index)); cell_cnt is counted back down to zero
 __global__ void __launch_bounds__(256)
-cell_scatter_kernel(const float* __restrict__ s, int Ns, const uint32_t* __restrict__ cell_id,
-                    const int* __restrict__ cell_start, int* __restrict__ cell_cnt, float4* __restrict__ sorted_pts) {
+cell_scatter_kernel(const float* __restrict__ s, int Ns_cap, const int* __restrict__ ns_dev,
+                    const uint32_t* __restrict__ cell_id, const int* __restrict__ cell_start,
+                    int* __restrict__ cell_cnt, float4* __restrict__ sorted_pts) {
+  const int Ns = dyn_rows(Ns_cap, ns_dev);
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Ns) return;
   uint32_t c = cell_id[i];
@@ -110,7 +114,8 @@ size_t radius_neighbors_workspace_bytes(int Ns, int B, float radius, const float
 }
 
 int radius_neighbors_build(const float* supports, const int* s_batch_len, int B, int Ns, float radius,
-                           const float* host_bbox, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                           const float* host_bbox, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                           const int* ns_dev) {
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "radius_neighbors: B=%d must be in [1,%d]", B, kMaxBatch);
   D3F_REQUIRE(radius > 0.f && Ns >= 0 && host_bbox != nullptr, D3F_ERR_INVALID,
               "radius_neighbors: radius=%g Ns=%d invalid or host_bbox missing", (double)radius, Ns);
@@ -130,11 +135,11 @@ int radius_neighbors_build(const float* supports, const int* s_batch_len, int B,
     D3F_CUDA(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * ((size_t)total + 1), stream));
     return D3F_OK;
   }
-  cell_count_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, w.s_start, B, g, w.cell_id, w.cell_cnt);
+  cell_count_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, ns_dev, w.s_start, B, g, w.cell_id, w.cell_cnt);
   D3F_LAUNCH_CHECK("cell_count_kernel");
   if (exclusive_scan_i32(w.cell_cnt, w.cell_start, (int)total, w.cell_start + total, w.scan_scratch, stream))
     return D3F_ERR_CUDA;
-  cell_scatter_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, w.cell_id, w.cell_start, w.cell_cnt,
+  cell_scatter_kernel<<<ceil_div(Ns, 256), 256, 0, stream>>>(supports, Ns, ns_dev, w.cell_id, w.cell_start, w.cell_cnt,
                                                              w.sorted_pts);
   D3F_LAUNCH_CHECK("cell_scatter_kernel");
   return D3F_OK;
@@ -181,9 +186,13 @@ __device__ __forceinline__ float sq_dist_rn(float qx, float qy, float qz, float4
 // FILL = false: counts only. FILL = true: sorted rows.
 template <bool FILL>
 __global__ void __launch_bounds__(kNbWarps * 32)
-radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__ q_start, int B, NbGrid g,
-                    const float4* __restrict__ sorted_pts, const int* __restrict__ cell_start, float r2, int cols, int pad_value,
-                    int* __restrict__ counts, int* __restrict__ out_max, int* __restrict__ out_idx) {
+radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restrict__ nq_dev,
+                    const int* __restrict__ q_start, int B, NbGrid g, const float4* __restrict__ sorted_pts,
+                    const int* __restrict__ cell_start, float r2, int cols, int pad_value_in,
+                    const int* __restrict__ pad_dev, int* __restrict__ counts, int* __restrict__ out_max,
+                    int* __restrict__ out_idx) {
+  const int Nq = dyn_rows(Nq_cap, nq_dev);
+  const int pad_value = pad_dev ? __ldg(pad_dev) : pad_value_in;   // the shadow index = number of supports (device)
   __shared__ int run_start[kNbWarps][9];
   __shared__ int run_prefix[kNbWarps][10];
   __shared__ Hit list[FILL ? kNbWarps : 1][FILL ? kNbListCap : 1];
@@ -357,7 +366,8 @@ radius_query_kernel(const float* __restrict__ q, int Nq, const int* __restrict__
 
 static int query_common(bool fill, const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                         const float* host_bbox, const void* workspace, int cols, int pad_value, int* counts,
-                        int* out_max, int* out_idx, cudaStream_t stream) {
+                        int* out_max, int* out_idx, cudaStream_t stream, const int* nq_dev = nullptr,
+                        const int* pad_dev = nullptr) {
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch && Nq >= 0 && radius > 0.f && host_bbox != nullptr, D3F_ERR_INVALID,
               "radius_neighbors: invalid arguments (B=%d Nq=%d radius=%g)", B, Nq, (double)radius);
   NbGrid g = make_grid(host_bbox, radius);
@@ -372,12 +382,12 @@ static int query_common(bool fill, const float* queries, const int* q_batch_len,
   float r2 = radius * radius;  // neighbors.cpp:226 (fp32 product)
   int blocks = ceil_div(Nq, kNbWarps);
   if (fill) {
-    radius_query_kernel<true><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, w.q_start, B, g, w.sorted_pts,
-                                                                    w.cell_start, r2, cols, pad_value,
+    radius_query_kernel<true><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, nq_dev, w.q_start, B, g, w.sorted_pts,
+                                                                    w.cell_start, r2, cols, pad_value, pad_dev,
                                                                     counts, out_max, out_idx);
   } else {
-    radius_query_kernel<false><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, w.q_start, B, g, w.sorted_pts,
-                                                                     w.cell_start, r2, 0, 0, counts,
+    radius_query_kernel<false><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, nq_dev, w.q_start, B, g, w.sorted_pts,
+                                                                     w.cell_start, r2, 0, 0, nullptr, counts,
                                                                      out_max, nullptr);
   }
   D3F_LAUNCH_CHECK("radius_query_kernel");
@@ -394,12 +404,12 @@ int radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq,
 
 int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                           const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const int* nq_dev, const int* pad_dev) {
   D3F_REQUIRE(cols >= 0 && (out_idx != nullptr || cols == 0 || Nq == 0), D3F_ERR_INVALID,
               "radius_neighbors_fill: cols=%d / null output", cols);
   if (cols == 0) return D3F_OK;
   return query_common(true, queries, q_batch_len, Nq, B, Ns, radius, host_bbox, workspace, cols, pad_value, nullptr,
-                      nullptr, out_idx, stream);
+                      nullptr, out_idx, stream, nq_dev, pad_dev);
 }
 
 }  // namespace d3f

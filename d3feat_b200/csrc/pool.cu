@@ -13,8 +13,9 @@ namespace d3f {
 // immediately while the flag is down, and produce the reference's result exactly when it is up.
 //
 // column-wise minimum via ordered-uint atomics; colmin_ord pre-set to 0xFFFFFFFF
-__global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x, int N, int C,
-                                                     unsigned* __restrict__ colmin_ord) {
+__global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x, int Ncap, const int* __restrict__ n_dev,
+                                                     int C, unsigned* __restrict__ colmin_ord) {
+  const int N = dyn_rows(Ncap, n_dev);
   __shared__ unsigned red[8][32];
   if (colmin_ord[C] != 0u) return;   // no row asked for the shadow value
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -34,8 +35,10 @@ __global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x
 // one warp per pooled row; lanes stride the channels (float4 when C % 4 == 0)
 template <int VEC>
 __global__ void __launch_bounds__(256)
-ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1, int N2, int H, int C,
+ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1cap, int N2cap,
+                    const int* __restrict__ n1_dev, const int* __restrict__ n2_dev, int H, int C,
                     unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
+  const int N1 = dyn_rows(N1cap, n1_dev), N2 = dyn_rows(N2cap, n2_dev);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N2) return;
   const int* row = inds + (size_t)warp * H;
@@ -72,9 +75,11 @@ ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, i
 
 // rows without any real neighbour := column minimum (only runs its body when the pooling kernel raised the flag)
 __global__ void __launch_bounds__(256)
-ind_max_pool_fix_kernel(const int* __restrict__ inds, int N1, int N2, int H, int C,
-                        const unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
+ind_max_pool_fix_kernel(const int* __restrict__ inds, int N1cap, int N2cap, const int* __restrict__ n1_dev,
+                        const int* __restrict__ n2_dev, int H, int C, const unsigned* __restrict__ colmin_ord,
+                        float* __restrict__ out) {
   if (colmin_ord[C] != 0u) return;
+  const int N1 = dyn_rows(N1cap, n1_dev), N2 = dyn_rows(N2cap, n2_dev);
   const int lane = threadIdx.x & 31;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < N2; r += (gridDim.x * blockDim.x) >> 5) {
     bool real = false;
@@ -88,7 +93,7 @@ ind_max_pool_fix_kernel(const int* __restrict__ inds, int N1, int N2, int H, int
 }
 
 int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out, void* workspace,
-                 size_t workspace_bytes, cudaStream_t stream) {
+                 size_t workspace_bytes, cudaStream_t stream, const int* n1_dev, const int* n2_dev) {
   D3F_REQUIRE(N1 >= 1 && N2 >= 0 && H >= 0 && C >= 1, D3F_ERR_INVALID, "ind_max_pool: bad shape N1=%d N2=%d H=%d C=%d",
               N1, N2, H, C);
   D3F_REQUIRE(workspace_bytes >= sizeof(unsigned) * ((size_t)C + 1), D3F_ERR_WORKSPACE,
@@ -98,20 +103,22 @@ int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, 
   D3F_CUDA(cudaMemsetAsync(colmin, 0xff, sizeof(unsigned) * ((size_t)C + 1), stream));
   int blocks = ceil_div(N2 * 32, 256);
   bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (v4) ind_max_pool_kernel<4><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, H, C, colmin, out);
-  else ind_max_pool_kernel<1><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, H, C, colmin, out);
+  if (v4) ind_max_pool_kernel<4><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, H, C, colmin, out);
+  else ind_max_pool_kernel<1><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, H, C, colmin, out);
   D3F_LAUNCH_CHECK("ind_max_pool_kernel");
   dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 64), 4 * kNumSMs));
-  colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, C, colmin);
+  colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, n1_dev, C, colmin);
   D3F_LAUNCH_CHECK("colmin_kernel");
-  ind_max_pool_fix_kernel<<<min(blocks, 4 * kNumSMs), 256, 0, stream>>>(inds, N1, N2, H, C, colmin, out);
+  ind_max_pool_fix_kernel<<<min(blocks, 4 * kNumSMs), 256, 0, stream>>>(inds, N1, N2, n1_dev, n2_dev, H, C, colmin, out);
   D3F_LAUNCH_CHECK("ind_max_pool_fix_kernel");
   return D3F_OK;
 }
 
 __global__ void __launch_bounds__(256)
-closest_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1, int N2, int ld, int C,
+closest_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1cap, int N2cap,
+                    const int* __restrict__ n1_dev, const int* __restrict__ n2_dev, int ld, int C,
                     float* __restrict__ out) {
+  const int N1 = dyn_rows(N1cap, n1_dev), N2 = dyn_rows(N2cap, n2_dev);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N2) return;
   int id = inds[(size_t)warp * ld];
@@ -119,16 +126,19 @@ closest_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, i
   for (int c = lane; c < C; c += 32) out[(size_t)warp * C + c] = shadow ? 0.f : x[(size_t)id * C + c];
 }
 
-int closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C, float* out, cudaStream_t stream) {
+int closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C, float* out, cudaStream_t stream,
+                 const int* n1_dev, const int* n2_dev) {
   D3F_REQUIRE(N1 >= 0 && N2 >= 0 && ld_inds >= 1 && C >= 1, D3F_ERR_INVALID, "closest_pool: bad shape");
   if (N2 == 0) return D3F_OK;
-  closest_pool_kernel<<<ceil_div(N2 * 32, 256), 256, 0, stream>>>(x, inds, N1, N2, ld_inds, C, out);
+  closest_pool_kernel<<<ceil_div(N2 * 32, 256), 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, ld_inds, C, out);
   D3F_LAUNCH_CHECK("closest_pool_kernel");
   return D3F_OK;
 }
 
-__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, int N, int C, float eps,
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, int Ncap,
+                                                           const int* __restrict__ n_dev, int C, float eps,
                                                            float* __restrict__ out) {
+  const int N = dyn_rows(Ncap, n_dev);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   float s = 0.f;
@@ -145,10 +155,10 @@ __global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restri
   for (int c = lane; c < C; c += 32) out[(size_t)warp * C + c] = x[(size_t)warp * C + c] * inv;
 }
 
-int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream_t stream) {
+int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream_t stream, const int* n_dev) {
   D3F_REQUIRE(N >= 0 && C >= 1, D3F_ERR_INVALID, "l2_normalize: bad shape");
   if (N == 0) return D3F_OK;
-  l2_normalize_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(x, N, C, eps, out);
+  l2_normalize_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(x, N, n_dev, C, eps, out);
   D3F_LAUNCH_CHECK("l2_normalize_kernel");
   return D3F_OK;
 }
@@ -158,8 +168,10 @@ int l2_normalize(const float* x, int N, int C, float eps, float* out, cudaStream
 // B stacked clouds: per-cloud max normalisation, density-invariant saliency softplus(x - mean of the neighbours whose
 // feature-row sum is non-zero), channel-max ratio, max over channels.
 __global__ void __launch_bounds__(256)
-cloud_max_kernel(const float* __restrict__ x, int N, int D, const int* __restrict__ start, int B,
-                 unsigned* __restrict__ cloud_max_ord, unsigned char* __restrict__ nonzero) {
+cloud_max_kernel(const float* __restrict__ x, int Ncap, const int* __restrict__ n_dev, int D,
+                 const int* __restrict__ start, int B, unsigned* __restrict__ cloud_max_ord,
+                 unsigned char* __restrict__ nonzero) {
+  const int N = dyn_rows(Ncap, n_dev);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   float m = -3.402823466e38f, s = 0.f;
@@ -180,9 +192,11 @@ cloud_max_kernel(const float* __restrict__ x, int N, int D, const int* __restric
 }
 
 __global__ void __launch_bounds__(256)
-detection_score_kernel(const float* __restrict__ x, const int* __restrict__ nb, int N, int H, int D,
-                       const int* __restrict__ start, int B, const unsigned* __restrict__ cloud_max_ord,
-                       const unsigned char* __restrict__ nonzero, float* __restrict__ score) {
+detection_score_kernel(const float* __restrict__ x, const int* __restrict__ nb, int Ncap,
+                       const int* __restrict__ n_dev, int H, int D, const int* __restrict__ start, int B,
+                       const unsigned* __restrict__ cloud_max_ord, const unsigned char* __restrict__ nonzero,
+                       float* __restrict__ score) {
+  const int N = dyn_rows(Ncap, n_dev);
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= N) return;
   // all neighbours of a point lie in its own cloud, so one scale serves the point and its neighbourhood
@@ -221,7 +235,8 @@ size_t detection_scores_workspace_bytes(int N, int B) {
 }
 
 int detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N, int H, int D,
-                     float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                     float* out_scores, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                     const int* n_dev) {
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch && N >= 0 && H >= 0 && D >= 1, D3F_ERR_INVALID, "detection_scores: bad shape");
   D3F_REQUIRE(workspace_bytes >= detection_scores_workspace_bytes(N, B), D3F_ERR_WORKSPACE, "detection_scores: workspace too small");
   if (N == 0) return D3F_OK;
@@ -232,17 +247,18 @@ int detection_scores(const float* feats, const int* neighbors, const int* length
   int rc = launch_batch_start(lengths, B, start, stream);
   if (rc) return rc;
   D3F_CUDA(cudaMemsetAsync(cmax, 0, sizeof(unsigned) * B, stream));
-  cloud_max_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(feats, N, D, start, B, cmax, nonzero);
+  cloud_max_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(feats, N, n_dev, D, start, B, cmax, nonzero);
   D3F_LAUNCH_CHECK("cloud_max_kernel");
-  detection_score_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(feats, neighbors, N, H, D, start, B, cmax, nonzero, out_scores);
+  detection_score_kernel<<<ceil_div(N * 32, 256), 256, 0, stream>>>(feats, neighbors, N, n_dev, H, D, start, B, cmax, nonzero, out_scores);
   D3F_LAUNCH_CHECK("detection_score_kernel");
   return D3F_OK;
 }
 
 __global__ void __launch_bounds__(256)
-affine_leaky_kernel(const float* __restrict__ x, long long total, int C, const float* __restrict__ scale,
-                    const float* __restrict__ shift, const float* __restrict__ residual, float alpha,
-                    float* __restrict__ out) {
+affine_leaky_kernel(const float* __restrict__ x, long long total_cap, const int* __restrict__ n_dev, int C,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ residual, float alpha, float* __restrict__ out) {
+  const long long total = n_dev ? min(total_cap, (long long)max(__ldg(n_dev), 0) * C) : total_cap;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % C);
     float y = x[i];
@@ -254,12 +270,12 @@ affine_leaky_kernel(const float* __restrict__ x, long long total, int C, const f
 }
 
 int affine_leaky(const float* x, int N, int C, const float* scale, const float* shift, const float* residual,
-                 float alpha, float* out, cudaStream_t stream) {
+                 float alpha, float* out, cudaStream_t stream, const int* n_dev) {
   D3F_REQUIRE(N >= 0 && C >= 1 && (scale == nullptr) == (shift == nullptr), D3F_ERR_INVALID, "affine_leaky: bad arguments");
   long long total = (long long)N * C;
   if (total == 0) return D3F_OK;
   int blocks = (int)min((total + 255) / 256, (long long)kNumSMs * 16);
-  affine_leaky_kernel<<<blocks, 256, 0, stream>>>(x, total, C, scale, shift, residual, alpha, out);
+  affine_leaky_kernel<<<blocks, 256, 0, stream>>>(x, total, n_dev, C, scale, shift, residual, alpha, out);
   D3F_LAUNCH_CHECK("affine_leaky_kernel");
   return D3F_OK;
 }

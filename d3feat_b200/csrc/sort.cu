@@ -8,8 +8,9 @@
 namespace d3f {
 
 __global__ void __launch_bounds__(kSortThreads)
-radix_count_kernel(const uint64_t* __restrict__ keys, int N, int shift, int nblocks,
+radix_count_kernel(const uint64_t* __restrict__ keys, int Ncap, const int* __restrict__ n_dev, int shift, int nblocks,
                    int* __restrict__ block_hist) {
+  const int N = dyn_rows(Ncap, n_dev);
   __shared__ int hist[256];
   hist[threadIdx.x] = 0;
   __syncthreads();
@@ -70,8 +71,9 @@ __global__ void __launch_bounds__(1024) scan_single_cta_kernel(int* __restrict__
 
 __global__ void __launch_bounds__(kSortThreads)
 radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int N, int shift,
-                     int nblocks, const int* __restrict__ block_base) {
+                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int Ncap,
+                     const int* __restrict__ n_dev, int shift, int nblocks, const int* __restrict__ block_base) {
+  const int N = dyn_rows(Ncap, n_dev);
   constexpr int kWarps = kSortThreads / 32;
   __shared__ int warp_cnt[kWarps][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -127,19 +129,19 @@ radix_scatter_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __res
   }
 }
 
-int radix_sort_pairs(const SortBuffers& buf, int N, int nbits, cudaStream_t stream) {
+int radix_sort_pairs(const SortBuffers& buf, int N, int nbits, cudaStream_t stream, const int* n_dev) {
   if (N <= 0) return 0;
   const int passes = sort_num_passes(nbits);
   const int nblocks = sort_num_blocks(N);
   int cur = 0;
   for (int p = 0; p < passes; ++p) {
     int shift = 8 * p;
-    radix_count_kernel<<<nblocks, kSortThreads, 0, stream>>>(buf.keys[cur], N, shift, nblocks, buf.block_hist);
+    radix_count_kernel<<<nblocks, kSortThreads, 0, stream>>>(buf.keys[cur], N, n_dev, shift, nblocks, buf.block_hist);
     D3F_LAUNCH_CHECK("radix_count_kernel");
     scan_single_cta_kernel<<<1, 1024, 0, stream>>>(buf.block_hist, 256 * nblocks);
     D3F_LAUNCH_CHECK("scan_single_cta_kernel");
     radix_scatter_kernel<<<nblocks, kSortThreads, 0, stream>>>(buf.keys[cur], buf.vals[cur], buf.keys[cur ^ 1],
-                                                               buf.vals[cur ^ 1], N, shift, nblocks,
+                                                               buf.vals[cur ^ 1], N, n_dev, shift, nblocks,
                                                                buf.block_hist);
     D3F_LAUNCH_CHECK("radix_scatter_kernel");
     cur ^= 1;
@@ -148,8 +150,10 @@ int radix_sort_pairs(const SortBuffers& buf, int N, int nbits, cudaStream_t stre
 }
 
 // ---- exclusive scan over N ints: per-CTA reduce -> single-CTA scan of CTA sums -> per-CTA scan -------
-__global__ void __launch_bounds__(256) scan_reduce_kernel(const int* __restrict__ in, int N,
+__global__ void __launch_bounds__(256) scan_reduce_kernel(const int* __restrict__ in, int Ncap,
+                                                          const int* __restrict__ n_dev,
                                                           int* __restrict__ block_sums) {
+  const int N = dyn_rows(Ncap, n_dev);
   __shared__ int ws[8];
   int base = blockIdx.x * 2048;
   int s = 0;
@@ -170,9 +174,11 @@ __global__ void __launch_bounds__(256) scan_reduce_kernel(const int* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, int N,
+__global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__ in, int* __restrict__ out, int Ncap,
+                                                         const int* __restrict__ n_dev,
                                                          const int* __restrict__ block_offsets, int nblocks,
                                                          int* __restrict__ total) {
+  const int N = dyn_rows(Ncap, n_dev);
   __shared__ int ws[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // thread t owns 8 consecutive elements
@@ -205,17 +211,18 @@ __global__ void __launch_bounds__(256) scan_apply_kernel(const int* __restrict__
   if (total != nullptr && blockIdx.x == nblocks - 1 && threadIdx.x == 255) *total = excl;
 }
 
-int exclusive_scan_i32(const int* in, int* out, int N, int* total, int* scratch, cudaStream_t stream) {
+int exclusive_scan_i32(const int* in, int* out, int N, int* total, int* scratch, cudaStream_t stream,
+                       const int* n_dev) {
   if (N <= 0) {
     if (total) D3F_CUDA(cudaMemsetAsync(total, 0, sizeof(int), stream));
     return 0;
   }
   int nblocks = scan_num_blocks(N);
-  scan_reduce_kernel<<<nblocks, 256, 0, stream>>>(in, N, scratch);
+  scan_reduce_kernel<<<nblocks, 256, 0, stream>>>(in, N, n_dev, scratch);
   D3F_LAUNCH_CHECK("scan_reduce_kernel");
   scan_single_cta_kernel<<<1, 1024, 0, stream>>>(scratch, nblocks);
   D3F_LAUNCH_CHECK("scan_single_cta_kernel");
-  scan_apply_kernel<<<nblocks, 256, 0, stream>>>(in, out, N, scratch, nblocks, total);
+  scan_apply_kernel<<<nblocks, 256, 0, stream>>>(in, out, N, n_dev, scratch, nblocks, total);
   D3F_LAUNCH_CHECK("scan_apply_kernel");
   return 0;
 }

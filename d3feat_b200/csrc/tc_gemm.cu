@@ -15,6 +15,7 @@
 #include <stdlib.h>
 
 #include "ops.cuh"
+#include "tc_common.cuh"
 
 namespace d3f {
 
@@ -22,103 +23,6 @@ constexpr int kTcBM = 128;       // rows per CTA (UMMA M)
 constexpr int kTcBK = 32;        // fp32 per k-chunk = one 128 B swizzle row
 constexpr int kTcProducerThreads = 128;
 constexpr int kTcThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, mma_sm100_desc.hpp):
-//   [0,14) start>>4, [16,30) LBO>>4 (=1, unused for swizzled K-major), [32,46) SBO>>4 (8 rows * 128 B = 1024 B),
-//   [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N>>3, M>>4
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// explicit shared-window accesses: the aligned stage pointer is derived through integer arithmetic, so plain C++
-// dereferences compile to generic LD.E / ST.E; these keep the hot loops on LDS / STS
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float lds32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-
-// round-to-nearest TF32 split: hi has 10 explicit mantissa bits, lo = x - hi exactly
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
-  lo = x - hi;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // W[K,N] row-major -> packed[Kpad/32][2][Npad][32]: for every 32-wide k-chunk a (hi, lo) pair of ready-made shared
@@ -181,26 +85,13 @@ struct TcSmem {
   static constexpr int kTotal = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// TMA 1D bulk copy global -> shared, completing `bytes` on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
-}
-
 template <int BN, int STAGES, int ACC>
 __global__ void __launch_bounds__(kTcThreads, STAGES == 1 ? 4 : ((STAGES == 2 && BN <= 64) ? 2 : 1))
 tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1, const float* __restrict__ Bp,
-               float* __restrict__ C, int M, int N, int K, int Kpad, int Npad, int chunks_per_split, Epilogue ep) {
+               float* __restrict__ C, int Mcap, int N, int K, int Kpad, int Npad, int chunks_per_split, Epilogue ep) {
+  // the split-K slabs are laid out with the launch capacity; the rows that exist come from device memory if given
+  const int M = ep.m_dev ? min(Mcap, max(__ldg(ep.m_dev) - ep.m_off, 0)) : Mcap;
+  if ((int)blockIdx.y * kTcBM >= M) return;   // CTA-uniform, before any barrier / TMEM allocation
   extern __shared__ uint8_t smem_raw[];
   using S = TcSmem<BN, STAGES>;
   constexpr int kStages = S::kStages;
@@ -215,7 +106,7 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
   // split-K: CTA z owns the k-chunks [kt0, kt0 + nk) and writes raw partial sums to its own [M,N] slab of C
   const int kt0 = blockIdx.z * chunks_per_split;
   const int nk = min(Kpad / kTcBK - kt0, chunks_per_split);
-  C += (size_t)blockIdx.z * M * N;
+  C += (size_t)blockIdx.z * Mcap * N;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -424,13 +315,15 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
 }
 
 // fixed-order reduction of the split-K partials + the block epilogue
-__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N,
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, int splits, int Mcap, int N,
                                                             Epilogue ep, float* __restrict__ C) {
+  const int M = ep.m_dev ? min(Mcap, max(__ldg(ep.m_dev) - ep.m_off, 0)) : Mcap;
+  const long long slab = (long long)Mcap * N;
   long long total = (long long)M * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int m = (int)(i / N), n = (int)(i % N);
     float y = 0.f;
-    for (int z = 0; z < splits; ++z) y += part[(size_t)z * total + i];
+    for (int z = 0; z < splits; ++z) y += part[(size_t)z * slab + i];
     if (ep.rowscale) y *= ep.rowscale[m];
     if (ep.bn_scale) y = fmaf(y, ep.bn_scale[n], ep.bn_shift[n]);
     if (ep.bias) y += ep.bias[n];
@@ -462,7 +355,7 @@ static int launch_tc_s(const float* A, const float* A2, int K1, const float* Bp,
   splits = ceil_div(nk, cps);
   Epilogue raw;
   raw.rowscale = nullptr; raw.bn_scale = nullptr; raw.bn_shift = nullptr; raw.bias = nullptr; raw.residual = nullptr;
-  raw.leaky_alpha = -1.f; raw.row_map = nullptr;
+  raw.leaky_alpha = -1.f; raw.row_map = nullptr; raw.m_dev = ep.m_dev; raw.m_off = ep.m_off;
   dim3 grid(Npad / BN, ceil_div(M, kTcBM), splits);
   tc_gemm_kernel<BN, STAGES, ACC><<<grid, kTcThreads, S::kTotal, stream>>>(A, A2, K1, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
   D3F_LAUNCH_CHECK("tc_gemm_kernel");

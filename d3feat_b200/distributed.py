@@ -19,7 +19,8 @@ def _world(group):
     return dist.get_world_size(group)
 
 
-def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group=None, max_fragments=None):
+def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group=None, max_fragments=None,
+                                  rows_dev=None):
     """Sync-free gather used on the hot path.
 
     local_desc: float32[R, D] stacked descriptors of this rank's fragments (R is the tensor's shape, host-known);
@@ -27,6 +28,8 @@ def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group
     on the host here; capacity: rows reserved per rank (>= R on every rank); max_fragments: fragments reserved per
     rank (>= F on every rank; default F, which then must be the same on all ranks -- with round-robin sharding that
     only holds when n_fragments % world == 0).
+    rows_dev (optional): int device scalar with the ACTUAL number of valid rows when local_desc is a capacity-sized
+    buffer whose row count only the device knows (the graph-replayed pipeline); it replaces R in the meta row.
     Returns (gathered [world, capacity, D], meta [world, 2 + max_fragments] int64 = [R, F, rows per fragment...,
     zero padding]), both on the device; no host synchronisation, two collectives (one of them a few bytes).
     """
@@ -43,11 +46,17 @@ def all_gather_descriptors_padded(local_desc, rows_per_fragment, capacity, group
     # copy, which synchronises the stream first (the host would wait for the whole encoder queued before this call
     # and the pyramid(i+1) || encoder(i) overlap would be lost on every rank)
     meta = torch.zeros((2 + Fmax,), dtype=torch.int64, device=dev)
-    meta[0:1].fill_(R)
+    if rows_dev is not None:
+        meta[0:1] = rows_dev.reshape(1).to(torch.int64)
+    else:
+        meta[0:1].fill_(R)
     meta[1:2].fill_(F)
     meta[2:2 + F] = rows_per_fragment.to(torch.int64)
-    padded = torch.zeros((capacity, D), dtype=local_desc.dtype, device=dev)
-    padded[:R] = local_desc
+    if R == capacity and local_desc.is_contiguous():
+        padded = local_desc                     # already a capacity-sized buffer: no staging copy
+    else:
+        padded = torch.zeros((capacity, D), dtype=local_desc.dtype, device=dev)
+        padded[:R] = local_desc
     if world == 1:
         return padded.unsqueeze(0), meta.unsqueeze(0)
     metas = torch.empty((world, meta.numel()), dtype=torch.int64, device=dev)

@@ -23,6 +23,14 @@ class KPFCNN:
         self.limits = [int(x) for x in neighborhood_limits]
         self.has_decoder = any("upsample" in b for b in config.architecture)
 
+    def build_inputs_static(self, buffers):
+        """Sync-free pyramid over the batch already sitting in buffers.points0 / lengths0 / n0 (see
+        pyramid.descriptor_input, static form). Every tensor is a whole capacity-sized buffer."""
+        inputs = pyramid.descriptor_input(self.config, buffers.points0, buffers.lengths0, self.limits, buffers=buffers,
+                                          static=True)
+        inputs["features"] = buffers.features0
+        return inputs
+
     def build_inputs(self, stacked_points, stacked_lengths, features=None, bbox=None, buffers=None):
         pts = stacked_points
         if not torch.is_tensor(pts):
@@ -165,3 +173,156 @@ class BatchPipeline:
         self.s_pyr.synchronize()
         self.s_enc.synchronize()
         self.keep = []
+
+
+class GraphPipeline:
+    """Throughput / latency mode without the host in the loop: the whole step is two CUDA graph launches.
+
+    The pyramid is built in its static form (capacity-sized launches, level sizes stay in device memory, no
+    device->host read), the encoder's kernels take their row counts from the same device counters, so the launch
+    sequence of a step depends only on the shape BUCKET (number of clouds, per-level capacities, scene bounds), not on
+    the batch. Per ring slot the pyramid and the encoder are captured once and then replayed:
+
+        pipe = GraphPipeline.for_batch(enc, points0, lengths0)     # one exact (synchronising) pass sizes the bucket
+        pipe.prime(points, lengths)                                # H2D / D2D copy into the slot + pyramid graph
+        for ...:
+            res, counts = pipe.step(next_points, next_lengths)     # encoder graph (i) || pyramid graph (i+1)
+        pipe.drain(); pipe.check()                                 # status bits: capacity overflow / points out of bounds
+
+    `res` is the slot's static output buffer [capacity of the last level, C] and `counts` the device int32 level sizes
+    (rows beyond counts[-1] are undefined); both stay valid until the slot is reused DEPTH steps later. Mirrors the
+    overlap the reference gets from tf.data prefetch (datasets/common.py:744-763)."""
+
+    DEPTH = 3
+
+    def __init__(self, enc, capacities, n_clouds, bbox, decoder=False, post=None):
+        self.enc, self.decoder, self.post = enc, decoder, post
+        dev = enc.device
+        self.caps = [int(c) for c in capacities]
+        self.n_clouds = int(n_clouds)
+        self.bbox = np.ascontiguousarray(bbox, np.float32)
+        self.s_pyr = torch.cuda.Stream(device=dev)
+        self.s_enc = torch.cuda.Stream(device=dev)
+        self.slots = [pyramid.PyramidBuffers(enc.config, enc.limits, self.caps, self.n_clouds, dev, bbox=self.bbox)
+                      for _ in range(self.DEPTH)]
+        self.g_pyr = [None] * self.DEPTH
+        self.g_enc = [None] * self.DEPTH
+        self.out = [None] * self.DEPTH          # (inputs, F, res) captured per slot
+        self.ready = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self.done = [None] * self.DEPTH
+        self.kernels_per_step = 0
+        self.n_loaded = 0
+        self.pending = None
+
+    @classmethod
+    def for_batch(cls, enc, points, lengths, slack=1.125, margin=0.05, **kw):
+        """Bucket from a representative batch: one exact pass gives the level sizes (capacities = sizes x slack) and
+        the scene bounds (its bbox inflated by `margin` of the extent on every side)."""
+        inputs = enc.build_inputs(points, lengths)
+        sizes = [int(p.shape[0]) for p in inputs["points"]]
+        pts = inputs["points"][0]
+        bb = pyramid.ops.host_bbox(pts)
+        ext = np.maximum(bb[3:] - bb[:3], 1e-3)
+        bb = np.concatenate([bb[:3] - margin * ext, bb[3:] + margin * ext]).astype(np.float32)
+        return cls(enc, pyramid.bucket_capacities(sizes, slack), int(lengths.shape[0]), bb, **kw)
+
+    # ---- one slot -----------------------------------------------------------------------------------------
+    def _run_pyramid(self, k):
+        return self.enc.build_inputs_static(self.slots[k])
+
+    def _run_encoder(self, inputs):
+        F = self.enc.encode(inputs)
+        res = self.enc.describe(inputs, F) if self.decoder else F[-1]
+        return F, res
+
+    def _capture(self, k):
+        """Eager warm-up of both halves on slot k (lazy one-time work: weight packing, BN folding, kernel attributes,
+        the library's auxiliary stream), then the two captures."""
+        from . import _lib
+        for _ in range(2):
+            with torch.cuda.stream(self.s_pyr):
+                inputs = self._run_pyramid(k)
+            self.s_enc.wait_stream(self.s_pyr)
+            with torch.cuda.stream(self.s_enc):
+                self._run_encoder(inputs)
+            self.s_pyr.wait_stream(self.s_enc)
+        torch.cuda.synchronize(self.enc.device)
+        n0 = _lib.launch_count()
+        gp = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gp, stream=self.s_pyr):
+            inputs = self._run_pyramid(k)
+        ge = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ge, stream=self.s_enc):
+            F, res = self._run_encoder(inputs)
+        self.kernels_per_step = _lib.launch_count() - n0
+        self.g_pyr[k], self.g_enc[k], self.out[k] = gp, ge, (inputs, F, res)
+
+    def _load(self, points, lengths, inputs_ready):
+        k = self.n_loaded % self.DEPTH
+        self.n_loaded += 1
+        if self.done[k] is not None:
+            self.done[k].synchronize()        # bounds the host's run-ahead to DEPTH steps (normally long complete)
+        buf = self.slots[k]
+        n0 = int(points.shape[0])
+        if n0 > buf.caps[0] or int(lengths.shape[0]) != self.n_clouds:
+            raise ValueError("GraphPipeline: batch (%d points, %d clouds) does not fit the bucket (%d, %d)" % (
+                n0, int(lengths.shape[0]), buf.caps[0], self.n_clouds))
+        if self.g_pyr[k] is None:             # first use of the slot: fill it, then capture its two graphs
+            buf.points0[:n0].copy_(torch.as_tensor(points), non_blocking=True)
+            buf.lengths0.copy_(torch.as_tensor(lengths), non_blocking=True)
+            buf.n0.fill_(n0)
+            torch.cuda.synchronize(self.enc.device)
+            self._capture(k)
+        self.s_pyr.wait_event(inputs_ready)
+        with torch.cuda.stream(self.s_pyr):
+            buf.points0[:n0].copy_(torch.as_tensor(points), non_blocking=True)
+            buf.lengths0.copy_(torch.as_tensor(lengths), non_blocking=True)
+            buf.n0.fill_(n0)
+            self.g_pyr[k].replay()
+            self.ready[k].record(self.s_pyr)
+        for t in (points, lengths):
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(self.s_pyr)
+        return k
+
+    def _mark_inputs(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.enc.device))
+        return ev
+
+    def prime(self, points, lengths):
+        self.pending = self._load(points, lengths, self._mark_inputs())
+
+    def step(self, next_points=None, next_lengths=None, pre=None):
+        """Replay encoder(current batch), then load + replay the pyramid of the next batch on the other stream.
+        Returns (result buffer, device level counts) of the current batch, ordered on the caller's stream."""
+        k = self.pending
+        cur = torch.cuda.current_stream(self.enc.device)
+        inputs_ready = self._mark_inputs() if next_points is not None else None
+        inputs, F, res = self.out[k]
+        with torch.cuda.stream(self.s_enc):
+            self.s_enc.wait_event(self.ready[k])
+            if pre is not None:
+                pre()
+            self.g_enc[k].replay()
+            if self.post is not None:
+                res = self.post(inputs, res)
+            ev = torch.cuda.Event()
+            ev.record(self.s_enc)
+            self.done[k] = ev
+        cur.wait_event(ev)
+        self.pending = self._load(next_points, next_lengths, inputs_ready) if next_points is not None else None
+        return res, self.slots[k].counts
+
+    def drain(self):
+        self.s_pyr.synchronize()
+        self.s_enc.synchronize()
+
+    def check(self):
+        """Raise if any replayed batch overflowed the bucket (synchronises)."""
+        self.drain()
+        for k, buf in enumerate(self.slots):
+            st = int(buf.status.item())
+            if st:
+                raise RuntimeError("GraphPipeline: slot %d status %d (%s)" % (
+                    k, st, "points outside the scene bounds" if st & 1 else "a level exceeded its capacity"))

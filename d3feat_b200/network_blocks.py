@@ -41,7 +41,16 @@ def weight_variable(shape):
     return w
 
 
-def ind_max_pool(x, inds):
+def _rows(inputs, level):
+    """Device scalar with the actual row count of pyramid level `level` when the pyramid was built in its static
+    (capacity-sized, sync-free) form, else None: the tensors then have exact shapes."""
+    rows = inputs.get("rows") if isinstance(inputs, dict) else None
+    if not rows or level >= len(rows):
+        return None
+    return rows[level]
+
+
+def ind_max_pool(x, inds, *, rows_x=None, rows_out=None):
     """:51-66 -- max over the pooled rows; shadow index -> column-wise minimum of x."""
     x, inds = x.contiguous(), inds.contiguous()
     N1, C = x.shape
@@ -50,29 +59,29 @@ def ind_max_pool(x, inds):
     ws = _lib.workspace(L.d3f_ind_max_pool_workspace_bytes(C), x.device)
     out = torch.empty((N2, C), dtype=torch.float32, device=x.device)
     _lib.check(L.d3f_ind_max_pool(_lib.ptr(x), _lib.ptr(inds), N1, N2, H, C, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                  _lib.stream()), "d3f_ind_max_pool")
+                                  _lib.stream(), _lib.ptr(rows_x), _lib.ptr(rows_out)), "d3f_ind_max_pool")
     return out
 
 
-def closest_pool(x, inds):
+def closest_pool(x, inds, *, rows_x=None, rows_out=None):
     """:69-83 -- features of the closest pooled point (first index column); shadow -> zeros."""
     x, inds = x.contiguous(), inds.contiguous()
     N1, C = x.shape
     N2, H = inds.shape
     out = torch.empty((N2, C), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().d3f_closest_pool(_lib.ptr(x), _lib.ptr(inds), N1, N2, H, C, _lib.ptr(out), _lib.stream()),
-               "d3f_closest_pool")
+    _lib.check(_lib.lib().d3f_closest_pool(_lib.ptr(x), _lib.ptr(inds), N1, N2, H, C, _lib.ptr(out), _lib.stream(),
+                                           _lib.ptr(rows_x), _lib.ptr(rows_out)), "d3f_closest_pool")
     return out
 
 
-def _affine_leaky(x, scale, shift, residual, alpha):
+def _affine_leaky(x, scale, shift, residual, alpha, rows=None):
     x = x.contiguous()
     N, C = x.shape
     out = torch.empty_like(x)
     _lib.check(_lib.lib().d3f_affine_leaky(_lib.ptr(x), N, C, _lib.ptr(scale), _lib.ptr(shift),
                                            _lib.ptr(residual.contiguous()) if residual is not None else None,
-                                           -1.0 if alpha is None else float(alpha), _lib.ptr(out), _lib.stream()),
-               "d3f_affine_leaky")
+                                           -1.0 if alpha is None else float(alpha), _lib.ptr(out), _lib.stream(),
+                                           _lib.ptr(rows)), "d3f_affine_leaky")
     return out
 
 
@@ -114,22 +123,24 @@ def _order(inputs, layer_ind):
 
 
 def KPConv(query_points, support_points, neighbors_indices, features, K_values, radius, config, *, epilogue=None,
-           query_order=None):
+           query_order=None, rows_q=None, rows_s=None):
     """:86-103."""
     extent = config.KP_extent * radius / config.density_parameter
     return conv_ops.KPConv(query_points, support_points, neighbors_indices, features, K_values,
                            fixed=config.fixed_kernel_points, KP_extent=extent, KP_influence=config.KP_influence,
-                           aggregation_mode=config.convolution_mode, epilogue=epilogue, query_order=query_order)
+                           aggregation_mode=config.convolution_mode, epilogue=epilogue, query_order=query_order,
+                           rows_q=rows_q, rows_s=rows_s)
 
 
 def KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values, radius, config, *,
-                      epilogue=None, query_order=None):
+                      epilogue=None, query_order=None, rows_q=None, rows_s=None):
     """:106-124."""
     extent = config.KP_extent * radius / config.density_parameter
     return conv_ops.KPConv_deformable(query_points, support_points, neighbors_indices, features, K_values,
                                       fixed=config.fixed_kernel_points, KP_extent=extent,
                                       KP_influence=config.KP_influence, aggregation_mode=config.convolution_mode,
-                                      modulated=config.modulated, epilogue=epilogue, query_order=query_order)
+                                      modulated=config.modulated, epilogue=epilogue, query_order=query_order,
+                                      rows_q=rows_q, rows_s=rows_s)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -144,41 +155,47 @@ def _no_training(training):
 def last_unary_block(layer_ind, inputs, features, radius, fdim, config, training):
     """:194-205."""
     w = weight_variable([int(features.shape[1]), 32])
-    return conv_ops.unary_convolution(features, w)
+    return conv_ops.unary_convolution(features, w, rows=_rows(inputs, layer_ind))
 
 
 def unary_block(layer_ind, inputs, features, radius, fdim, config, training):
     """:207-219 -- 1x1 conv + BN + LeakyReLU (one kernel)."""
     _no_training(training)
     w = weight_variable([int(features.shape[1]), fdim])
-    return conv_ops.unary_convolution(features, w, epilogue=_bn_epilogue(config, 0.2))
+    return conv_ops.unary_convolution(features, w, epilogue=_bn_epilogue(config, 0.2), rows=_rows(inputs, layer_ind))
 
 
 def simple_block(layer_ind, inputs, features, radius, fdim, config, training):
     """:222-244."""
     _no_training(training)
     w = weight_variable([config.num_kernel_points, int(features.shape[1]), fdim])
+    r0 = _rows(inputs, layer_ind)
     return KPConv(inputs["points"][layer_ind], inputs["points"][layer_ind], inputs["neighbors"][layer_ind], features,
-                  w, radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind))
+                  w, radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind),
+                  rows_q=r0, rows_s=r0)
 
 
 def _resnetb(layer_ind, inputs, features, radius, fdim, config, training, strided, deformable):
     _no_training(training)
     conv = KPConv_deformable if deformable else KPConv
+    r_in = _rows(inputs, layer_ind)                                   # rows of this level
+    r_out = _rows(inputs, layer_ind + 1) if strided else r_in         # rows the block produces
     with variable_scope("conv1"):
         w = weight_variable([int(features.shape[1]), fdim // 2])
-        x = conv_ops.unary_convolution(features, w, epilogue=_bn_epilogue(config, 0.2))
+        x = conv_ops.unary_convolution(features, w, epilogue=_bn_epilogue(config, 0.2), rows=r_in)
     with variable_scope("conv2"):
         w = weight_variable([config.num_kernel_points, int(x.shape[1]), fdim // 2])
         if strided:
             x = conv(inputs["points"][layer_ind + 1], inputs["points"][layer_ind], inputs["pools"][layer_ind], x, w,
-                     radius, config, epilogue=_bn_epilogue(config, 0.2))
+                     radius, config, epilogue=_bn_epilogue(config, 0.2), rows_q=r_out, rows_s=r_in)
         else:
             x = conv(inputs["points"][layer_ind], inputs["points"][layer_ind], inputs["neighbors"][layer_ind], x, w,
-                     radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind))
+                     radius, config, epilogue=_bn_epilogue(config, 0.2), query_order=_order(inputs, layer_ind),
+                     rows_q=r_in, rows_s=r_in)
     pair = None
     with variable_scope("shortcut"):
-        shortcut = ind_max_pool(features, inputs["pools"][layer_ind]) if strided else features
+        shortcut = (ind_max_pool(features, inputs["pools"][layer_ind], rows_x=r_in, rows_out=r_out) if strided
+                    else features)
         if int(shortcut.shape[1]) != 2 * fdim:
             w_s = weight_variable([int(shortcut.shape[1]), 2 * fdim])
             pair = (w_s, _bn_epilogue(config, None)[:2])
@@ -187,9 +204,9 @@ def _resnetb(layer_ind, inputs, features, radius, fdim, config, training, stride
         if pair is not None:
             # conv3 + BN, shortcut unary + BN, add, LeakyReLU (:343-368) as one GEMM over the concatenated K
             return conv_ops.unary_pair_convolution(x, w, _bn_epilogue(config, None)[:2], shortcut, pair[0], pair[1],
-                                                   0.2)
+                                                   0.2, rows=r_out)
         # conv3 + BN + shortcut add + LeakyReLU in one kernel
-        return conv_ops.unary_convolution(x, w, epilogue=_bn_epilogue(config, 0.2), residual=shortcut)
+        return conv_ops.unary_convolution(x, w, epilogue=_bn_epilogue(config, 0.2), residual=shortcut, rows=r_out)
 
 
 def resnetb_block(layer_ind, inputs, features, radius, fdim, config, training):
@@ -215,7 +232,8 @@ def resnetb_deformable_strided_block(layer_ind, inputs, features, radius, fdim, 
 def nearest_upsample_block(layer_ind, inputs, features, radius, fdim, config, training):
     """:971-979."""
     with variable_scope("nearest_upsample"):
-        return closest_pool(features, inputs["upsamples"][layer_ind - 1])
+        return closest_pool(features, inputs["upsamples"][layer_ind - 1], rows_x=_rows(inputs, layer_ind),
+                            rows_out=_rows(inputs, layer_ind - 1))
 
 
 def get_block_ops(block_name):
@@ -270,7 +288,7 @@ def assemble_CNN_blocks(inputs, config, dropout_prob):
     return F
 
 
-def detection_scores(features, neighbors, lengths):
+def detection_scores(features, neighbors, lengths, *, rows=None):
     """Detection branch of models/D3Feat.py:67-115 on the decoder output BEFORE l2 normalisation: per-cloud max
     normalisation, softplus(x - mean over the non-zero neighbours), channel-max ratio, max over channels -> [N, 1].
     The reference hard-codes two clouds per batch (anchor || positive); here any number of stacked clouds."""
@@ -283,7 +301,8 @@ def detection_scores(features, neighbors, lengths):
     lib = _lib.lib()
     ws = _lib.workspace(lib.d3f_detection_scores_workspace_bytes(N, B), x.device)
     _lib.check(lib.d3f_detection_scores(_lib.ptr(x), _lib.ptr(nbr), _lib.ptr(lens), B, N, H, D, _lib.ptr(out),
-                                        _lib.ptr(ws), ws.numel(), _lib.stream()), "d3f_detection_scores")
+                                        _lib.ptr(ws), ws.numel(), _lib.stream(), _lib.ptr(rows)),
+               "d3f_detection_scores")
     return out
 
 
@@ -320,7 +339,7 @@ def assemble_FCNN_decoder(inputs, config, F, dropout_prob=1.0, with_scores=False
             features = torch.cat((features, F[layer]), dim=1)
     out = torch.empty_like(features)
     _lib.check(_lib.lib().d3f_l2_normalize(_lib.ptr(features.contiguous()), features.shape[0], features.shape[1], 1e-10,
-                                           _lib.ptr(out), _lib.stream()), "d3f_l2_normalize")
+                                           _lib.ptr(out), _lib.stream(), _lib.ptr(_rows(inputs, 0))), "d3f_l2_normalize")
     if with_scores:
-        return out, detection_scores(features, inputs["neighbors"][0], inputs["lengths"][0])
+        return out, detection_scores(features, inputs["neighbors"][0], inputs["lengths"][0], rows=_rows(inputs, 0))
     return out

@@ -91,24 +91,38 @@ def _ptr_array(tensors):
 
 class PyramidBuffers:
     """Pre-allocated output matrices + workspace of one pyramid (a slot of BatchPipeline's ring): steady-state batches
-    then touch no allocator at all. Rows are sized for `capacity` level-0 points (every level gets the level-0
-    capacity: a subsampled level can never have more points than its parent)."""
+    then touch no allocator at all.
 
-    def __init__(self, config, neighborhood_limits, capacity, n_clouds, device):
+    capacity: int (level-0 rows; every deeper level gets the same capacity -- a subsampled level can never have more
+    points than its parent) or a per-level list (tight buckets for the static form, where launch grids are sized by
+    capacity). `counts` (int32[L], device) receives the actual level sizes, `status` (int32[1]) the static form's
+    error bits, `points0` / `lengths0` / `features0` are the static form's input buffers."""
+
+    def __init__(self, config, neighborhood_limits, capacity, n_clouds, device, bbox=None):
         levels = _level_radii(config)
         L = len(levels)
         i32, f32 = torch.int32, torch.float32
-        self.capacity, self.n_clouds, self.device = int(capacity), int(n_clouds), device
+        self.n_clouds, self.device = int(n_clouds), device
+        self.caps = ([max(int(c), 1) for c in capacity] if isinstance(capacity, (list, tuple))
+                     else [max(int(capacity), 1)] * L)
+        assert len(self.caps) == L
+        self.capacity = self.caps[0]
         self.limits = [int(neighborhood_limits[l]) for l in range(L)]
-        cap = max(self.capacity, 1)
-        self.pts = [None] + [torch.empty((cap, 3), dtype=f32, device=device) for _ in range(1, L)]
+        self.pts = [None] + [torch.empty((self.caps[l], 3), dtype=f32, device=device) for l in range(1, L)]
         self.len = [None] + [torch.empty((n_clouds,), dtype=i32, device=device) for _ in range(1, L)]
-        self.nb = [torch.empty((cap, self.limits[l]), dtype=i32, device=device) if levels[l]["conv_r"] is not None
-                   else None for l in range(L)]
-        self.pool = [torch.empty((cap, self.limits[l]), dtype=i32, device=device) if levels[l]["dl"] is not None
-                     else None for l in range(L)]
-        self.up = [torch.empty((cap, self.limits[l]), dtype=i32, device=device) if levels[l]["dl"] is not None
-                   else None for l in range(L)]
+        self.nb = [torch.empty((self.caps[l], self.limits[l]), dtype=i32, device=device)
+                   if levels[l]["conv_r"] is not None else None for l in range(L)]
+        self.pool = [torch.empty((self.caps[l + 1], self.limits[l]), dtype=i32, device=device)
+                     if levels[l]["dl"] is not None and l + 1 < L else None for l in range(L)]
+        self.up = [torch.empty((self.caps[l], self.limits[l]), dtype=i32, device=device)
+                   if levels[l]["dl"] is not None and l + 1 < L else None for l in range(L)]
+        self.counts = torch.zeros((MAX_LEVELS,), dtype=i32, device=device)
+        self.status = torch.zeros((1,), dtype=i32, device=device)
+        self.n0 = torch.zeros((1,), dtype=i32, device=device)
+        self.points0 = torch.zeros((self.caps[0], 3), dtype=f32, device=device)
+        self.lengths0 = torch.zeros((n_clouds,), dtype=i32, device=device)
+        self.features0 = torch.ones((self.caps[0], config.in_features_dim), dtype=f32, device=device)
+        self.bbox = None if bbox is None else np.ascontiguousarray(bbox, np.float32)
         self.ws = None
 
     def fits(self, n_points, n_clouds, limits):
@@ -120,17 +134,33 @@ class PyramidBuffers:
         return self.ws
 
 
-def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limits, bbox=None, buffers=None):
+def bucket_capacities(level_sizes, slack=1.125, quantum=256):
+    """Per-level capacities of a shape bucket from the level sizes of a representative batch."""
+    return [int(-(-int(n * slack + 64) // quantum) * quantum) for n in level_sizes]
+
+
+def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limits, bbox=None, buffers=None,
+                     static=False):
     """Returns the dict the blocks consume: points[L], neighbors[L], pools[L], upsamples[L], lengths[L]
     (placeholders of the reference's shapes at the last level, :1374-1377).
 
     neighborhood_limits: per-level column caps (Dataset.neighborhood_limits). Neighbour matrices are emitted
     with exactly `limit` columns, padded with the shadow index; when the true maximum count is below the
     limit the extra columns are all-shadow and do not change any downstream result.
+
+    static=True (needs `buffers` with a bbox): the sync-free form. Nothing is read back from the device; every returned
+    tensor is a whole capacity-sized buffer and inputs["rows"][l] is a device scalar with the level's actual row count
+    (inputs["counts"], inputs["status"] hold all of them / the error bits). stacked_points / stacked_lengths must
+    already be buffers.points0 / buffers.lengths0 (the caller copies each batch into them) with buffers.n0 set.
+    The launch sequence is then the same for every batch of the bucket -- it can be captured in a CUDA graph.
     """
     dev = stacked_points.device
     pts = _lib.f32(stacked_points, dev)
     lens = _lib.i32(stacked_lengths, dev)
+    if static:
+        if buffers is None or buffers.bbox is None:
+            raise ValueError("pyramid: the static form needs pre-allocated buffers with a scene bbox")
+        bbox = buffers.bbox
     if bbox is None:
         bbox = ops.host_bbox(pts)
     bb = np.ascontiguousarray(bbox, dtype=np.float32)
@@ -140,15 +170,13 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
     N0, B = int(pts.shape[0]), int(lens.shape[0])
     # a subsampled level can never have more points than its parent: every level gets the level-0 capacity
     cap = [max(N0, 1)] * L
-    cap_arr = (C.c_int * L)(*cap)
     lib = _lib.lib()
     i32, f32 = torch.int32, torch.float32
     if buffers is not None:
         if not buffers.fits(N0, B, [neighborhood_limits[l] for l in range(L)]):
             raise ValueError("pyramid: buffers (capacity %d, %d clouds) do not fit this batch (%d points, %d clouds)"
                              % (buffers.capacity, buffers.n_clouds, N0, B))
-        cap = [max(buffers.capacity, 1)] * L
-        cap_arr = (C.c_int * L)(*cap)
+        cap = list(buffers.caps)
         out_pts, out_len, out_nb, out_pool, out_up = buffers.pts, buffers.len, buffers.nb, buffers.pool, buffers.up
     else:
         out_pts = [None] + [torch.empty((cap[l], 3), dtype=f32, device=dev) for l in range(1, L)]
@@ -156,22 +184,42 @@ def descriptor_input(config, stacked_points, stacked_lengths, neighborhood_limit
         lim = [int(neighborhood_limits[l]) for l in range(L)]
         out_nb = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["conv_r"] is not None else None
                   for l in range(L)]
-        out_pool = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
-                    for l in range(L)]
-        out_up = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev) if levels[l]["dl"] is not None else None
-                  for l in range(L)]
+        out_pool = [torch.empty((cap[l + 1], lim[l]), dtype=i32, device=dev)
+                    if levels[l]["dl"] is not None and l + 1 < L else None for l in range(L)]
+        out_up = [torch.empty((cap[l], lim[l]), dtype=i32, device=dev)
+                  if levels[l]["dl"] is not None and l + 1 < L else None for l in range(L)]
+    cap_arr = (C.c_int * L)(*cap)
     nbytes = lib.d3f_pyramid_workspace_bytes(B, C.byref(spec), cap_arr, bbp)
     if nbytes == 0:
         raise _lib.D3FError("pyramid: hash grid too large for bbox %s" % bb.tolist())
     ws = buffers.workspace(nbytes) if buffers is not None else _lib.workspace(nbytes, dev)
-    sizes = (C.c_int * L)()
-    _lib.check(lib.d3f_pyramid_build(_lib.ptr(pts), _lib.ptr(lens), B, N0, C.byref(spec), bbp, _ptr_array(out_pts),
-                                     _ptr_array(out_len), _ptr_array(out_nb), _ptr_array(out_pool),
-                                     _ptr_array(out_up), cap_arr, sizes, _lib.ptr(ws), ws.numel(), _lib.stream()),
-               "d3f_pyramid_build")
-    n = [int(sizes[l]) for l in range(L)]
     empty_i = torch.zeros((0, 1), dtype=i32, device=dev)
     out = dict(points=[], neighbors=[], pools=[], upsamples=[], lengths=[], orders=[])
+    if static:
+        _lib.check(lib.d3f_pyramid_build(_lib.ptr(pts), _lib.ptr(lens), B, N0, C.byref(spec), bbp,
+                                         _ptr_array(out_pts), _ptr_array(out_len), _ptr_array(out_nb),
+                                         _ptr_array(out_pool), _ptr_array(out_up), cap_arr, None, _lib.ptr(ws),
+                                         ws.numel(), _lib.stream(), _lib.ptr(buffers.counts),
+                                         _lib.ptr(buffers.status), _lib.ptr(buffers.n0)), "d3f_pyramid_build")
+        for l in range(L):
+            out["points"].append(pts if l == 0 else out_pts[l])
+            out["lengths"].append(lens if l == 0 else out_len[l])
+            out["neighbors"].append(out_nb[l] if out_nb[l] is not None else empty_i)
+            out["pools"].append(out_pool[l] if out_pool[l] is not None else empty_i)
+            out["upsamples"].append(out_up[l] if out_up[l] is not None else empty_i)
+            out["orders"].append(torch.zeros((0,), dtype=i32, device=dev))
+        out["rows"] = [buffers.counts[l:l + 1] for l in range(L)]
+        out["counts"], out["status"] = buffers.counts, buffers.status
+        return out
+    sizes = (C.c_int * L)()
+    counts = buffers.counts if buffers is not None else None
+    status = buffers.status if buffers is not None else None
+    _lib.check(lib.d3f_pyramid_build(_lib.ptr(pts), _lib.ptr(lens), B, N0, C.byref(spec), bbp, _ptr_array(out_pts),
+                                     _ptr_array(out_len), _ptr_array(out_nb), _ptr_array(out_pool),
+                                     _ptr_array(out_up), cap_arr, sizes, _lib.ptr(ws), ws.numel(), _lib.stream(),
+                                     _lib.ptr(counts), _lib.ptr(status), None),
+               "d3f_pyramid_build")
+    n = [int(sizes[l]) for l in range(L)]
     for l in range(L):
         out["points"].append(pts if l == 0 else out_pts[l][:n[l]])
         out["lengths"].append(lens if l == 0 else out_len[l])

@@ -121,8 +121,17 @@ int d3f_radius_neighbors_fill(const float* queries, const int* q_batch_len, int 
  * if sub_dl[l] > 0: points_{l+1} = grid_subsample(points_l, sub_dl[l]); pools[l] = search(points_{l+1}, points_l,
  * pool_radius[l]); upsamples[l] = search(points_l, points_{l+1}, up_radius[l]). Every index matrix has exactly
  * limit[l] columns (nearest first, padded with the number of supports). Output buffers are caller-allocated with
- * `capacity[l]` rows per level; out_level_sizes (HOST int[n_levels]) receives the actual row counts. The call
- * synchronises the stream once per subsampled level (the next level's launch sizes depend on the cell count).
+ * `capacity[l]` rows per level.
+ *   Exact form (out_level_sizes != NULL, a HOST int[n_levels]): receives the actual row counts; the call synchronises
+ *   the stream once per subsampled level (the next level's launch sizes depend on the cell count) -- what the TF ops
+ *   do (their output shapes are data dependent, tf_batch_subsampling.cpp:99-104).
+ *   Static form (out_level_sizes == NULL): no device->host read at all. Launches are sized by capacity[l], every
+ *   kernel reads its row count from d_counts[l] (DEVICE int[n_levels], written by this call), conditions that the exact
+ *   form reports as errors are OR-ed into *d_status (DEVICE int: bit 0 = points outside host_bbox, bit 1 = a level
+ *   has more cells than capacity[l+1]). The launch sequence depends only on (B, capacity, spec, host_bbox), so a
+ *   caller may capture it in a CUDA graph and replay it for every batch of the same bucket. d_counts[0] = N0, or
+ *   *n0_dev when n0_dev != NULL (the level-0 count kept on the device; N0 is then the capacity of `points`).
+ *   d_counts / d_status may be NULL in the exact form.
  * ------------------------------------------------------------------------------------------- */
 #define D3F_MAX_LEVELS 8
 typedef struct {
@@ -139,7 +148,16 @@ int d3f_pyramid_build(const float* points, const int* lengths, int B, int N0,
                       const d3f_pyramid_spec* spec, const float* host_bbox, float* const* out_points,
                       int* const* out_lengths, int* const* out_neighbors, int* const* out_pools,
                       int* const* out_upsamples, const int* capacity, int* out_level_sizes,
-                      void* workspace, size_t workspace_bytes, d3f_stream_t stream);
+                      void* workspace, size_t workspace_bytes, d3f_stream_t stream, int* d_counts,
+                      int* d_status, const int* n0_dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-side row counts. Every row-wise entry point below takes trailing `const int* ..._dev` arguments (all may
+ * be NULL). When given, the integer row count (Nq / Ns / N / N1 / N2) is the CAPACITY of the buffers and of the launch,
+ * and the kernels read the actual count from device memory (e.g. &d_counts[l] of d3f_pyramid_build) -- rows beyond
+ * it are neither read nor written, and the shadow index is the actual count. This is what lets a whole step be
+ * enqueued (or graph-replayed) without the host ever knowing the level sizes.
+ * ------------------------------------------------------------------------------------------- */
 
 /* ---------------------------------------------------------------------------------------------
  * Static weights for the tensor-core path. A weight matrix W[K,N] (row-major; for KPConv the [K*Cin, Cout]
@@ -160,6 +178,8 @@ int d3f_pack_weight(const float* W, int K, int N, float* packed, d3f_stream_t st
  *   the caller: scale = gamma/sqrt(var+1e-6), shift = beta - mean*scale), then + bias[c] (if
  *   bias != NULL), then LeakyReLU(leaky_alpha) if leaky_alpha >= 0 (pass -1 for none).
  *   shadow_xyz: coordinate of the shadow support (1e6 rigid :190, 1000 deformable :414).
+ *   K = num_kernel_points (utils/config.py): any value in [1, 64]; K = 15 (the D3Feat configuration) runs the
+ *   specialised tensor-core kernels, other values a generic CUDA-core stage 1.
  * ------------------------------------------------------------------------------------------- */
 size_t d3f_kpconv_workspace_bytes(int Nq, int Ns, int H, int K, int Cin, int Cout);
 int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const float* feat,
@@ -168,7 +188,7 @@ int d3f_kpconv_forward(const float* q, const float* s, const int* idx, const flo
                        int Cout, float extent, int influence, int mode, int normalize,
                        const float* bn_scale, const float* bn_shift, const float* bias,
                        float leaky_alpha, float* out, void* workspace, size_t workspace_bytes,
-                       d3f_stream_t stream);
+                       d3f_stream_t stream, const int* nq_dev, const int* ns_dev);
 
 /* Deformable KPConv second stage (KPConv_deform_ops, :379-499): per-query kernel points
  * Kp + offsets[n,K,3]; influence distance /extent (no factor 2); neighbours in range of no kernel
@@ -180,7 +200,7 @@ int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, co
                               float extent, int influence, int mode, const float* bn_scale,
                               const float* bn_shift, const float* bias, float leaky_alpha,
                               float* out, void* workspace, size_t workspace_bytes,
-                              d3f_stream_t stream);
+                              d3f_stream_t stream, const int* nq_dev, const int* ns_dev);
 
 /* ---------------------------------------------------------------------------------------------
  * Unary convolution (features @ W) with fused epilogue:
@@ -189,20 +209,23 @@ int d3f_kpconv_deform_forward(const float* q, const float* s, const int* idx, co
  * ------------------------------------------------------------------------------------------- */
 int d3f_unary_forward(const float* x, const float* W, const float* W_packed, int N, int Cin, int Cout,
                       const float* bn_scale, const float* bn_shift, const float* bias,
-                      const float* residual, float leaky_alpha, float* out, d3f_stream_t stream);
+                      const float* residual, float leaky_alpha, float* out, d3f_stream_t stream,
+                      const int* n_dev);
 
 /* out[N2,C] = max_h x'[inds[n,h]] with x' = x || colmin(x) (shadow index = N1).
  * workspace: C floats. */
 size_t d3f_ind_max_pool_workspace_bytes(int C);
 int d3f_ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, float* out,
-                     void* workspace, size_t workspace_bytes, d3f_stream_t stream);
+                     void* workspace, size_t workspace_bytes, d3f_stream_t stream, const int* n1_dev,
+                     const int* n2_dev);
 
 /* out[N2,C] = x'[inds[n,0]] with x' = x || zeros. `ld_inds` = row stride of inds (H). */
 int d3f_closest_pool(const float* x, const int* inds, int N1, int N2, int ld_inds, int C,
-                     float* out, d3f_stream_t stream);
+                     float* out, d3f_stream_t stream, const int* n1_dev, const int* n2_dev);
 
 /* out[n,:] = x[n,:] * rsqrt(max(sum x^2, eps)) (tf.nn.l2_normalize, models/D3Feat.py:65) */
-int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream);
+int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_stream_t stream,
+                     const int* n_dev);
 
 /* Two unary convolutions that are summed -- the tail of every resnetb block (network_blocks.py:343-368: conv3 + BN,
  * shortcut unary + BN, add, LeakyReLU) -- as ONE tensor-core GEMM over the concatenated K:
@@ -210,7 +233,8 @@ int d3f_l2_normalize(const float* x, int N, int C, float eps, float* out, d3f_st
  * are the two weight matrices with their batch-norm scales folded in, shift = the sum of the two BN shifts.
  * Neither the shortcut tensor nor the [x1 | x2] concatenation is ever materialised. Cin1 % 32 == 0, Cin2 % 4 == 0. */
 int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2, const float* W_packed, int N,
-                           int Cout, const float* shift, float leaky_alpha, float* out, d3f_stream_t stream);
+                           int Cout, const float* shift, float leaky_alpha, float* out, d3f_stream_t stream,
+                           const int* n_dev);
 
 /* Detection score of D3Feat (models/D3Feat.py:67-115) for B stacked clouds: feats[N,D] are the decoder outputs BEFORE
  * l2 normalisation, neighbors[N,H] the level-0 conv neighbours (shadow index = N), lengths[B] the stack lengths.
@@ -218,13 +242,14 @@ int d3f_unary_pair_forward(const float* x1, int Cin1, const float* x2, int Cin2,
 size_t d3f_detection_scores_workspace_bytes(int N, int B);
 int d3f_detection_scores(const float* feats, const int* neighbors, const int* lengths, int B, int N,
                          int H, int D, float* out_scores, void* workspace, size_t workspace_bytes,
-                         d3f_stream_t stream);
+                         d3f_stream_t stream, const int* n_dev);
 
 /* Stand-alone block epilogue for callers that do not use the fused forms
  * (models/network_blocks.py:149-165 batch_norm inference form, :185-186 leaky_relu, :368 residual add):
  * y = x*scale[c] + shift[c] (if scale) ; y += residual (if) ; LeakyReLU(leaky_alpha) if >= 0. */
 int d3f_affine_leaky(const float* x, int N, int C, const float* scale, const float* shift,
-                     const float* residual, float leaky_alpha, float* out, d3f_stream_t stream);
+                     const float* residual, float leaky_alpha, float* out, d3f_stream_t stream,
+                     const int* n_dev);
 
 #ifdef __cplusplus
 }

@@ -23,30 +23,32 @@ def record_ops():
     orig = dict(kp=co.KPConv_ops, kd=co.KPConv_deform_ops, un=co.unary_convolution, up=co.unary_pair_convolution,
                 mp=nb.ind_max_pool)
 
-    def kp(q, s, idx, f, Kp, W, extent, infl, mode, *, epilogue=None, bias=None, query_order=None):
-        out = orig["kp"](q, s, idx, f, Kp, W, extent, infl, mode, epilogue=epilogue, bias=bias, query_order=query_order)
+    def kp(q, s, idx, f, Kp, W, extent, infl, mode, *, epilogue=None, bias=None, query_order=None, **rows):
+        out = orig["kp"](q, s, idx, f, Kp, W, extent, infl, mode, epilogue=epilogue, bias=bias, query_order=query_order,
+                         **rows)
         tr.records.append(dict(op="kpconv", q=q, s=s, idx=idx, f=f, Kp=Kp, W=W, extent=extent, infl=infl, mode=mode,
                                epilogue=epilogue, bias=bias, out=out))
         return out
 
-    def kd(q, s, idx, f, Kp, off, mod, W, extent, infl, mode, *, epilogue=None, query_order=None):
-        out = orig["kd"](q, s, idx, f, Kp, off, mod, W, extent, infl, mode, epilogue=epilogue, query_order=query_order)
+    def kd(q, s, idx, f, Kp, off, mod, W, extent, infl, mode, *, epilogue=None, query_order=None, **rows):
+        out = orig["kd"](q, s, idx, f, Kp, off, mod, W, extent, infl, mode, epilogue=epilogue, query_order=query_order,
+                         **rows)
         tr.records.append(dict(op="kpconv_deform", q=q, s=s, idx=idx, f=f, Kp=Kp, off=off, mod=mod, W=W, extent=extent,
                                infl=infl, mode=mode, epilogue=epilogue, out=out))
         return out
 
-    def un(x, w, *, epilogue=None, residual=None):
-        out = orig["un"](x, w, epilogue=epilogue, residual=residual)
+    def un(x, w, *, epilogue=None, residual=None, rows=None):
+        out = orig["un"](x, w, epilogue=epilogue, residual=residual, rows=rows)
         tr.records.append(dict(op="unary", x=x, w=w, epilogue=epilogue, residual=residual, out=out))
         return out
 
-    def up(x1, w1, a1, x2, w2, a2, alpha):
-        out = orig["up"](x1, w1, a1, x2, w2, a2, alpha)
+    def up(x1, w1, a1, x2, w2, a2, alpha, *, rows=None):
+        out = orig["up"](x1, w1, a1, x2, w2, a2, alpha, rows=rows)
         tr.records.append(dict(op="unary_pair", x1=x1, w1=w1, a1=a1, x2=x2, w2=w2, a2=a2, alpha=alpha, out=out))
         return out
 
-    def mp(x, inds):
-        out = orig["mp"](x, inds)
+    def mp(x, inds, **rows):
+        out = orig["mp"](x, inds, **rows)
         tr.records.append(dict(op="max_pool", x=x, inds=inds, out=out))
         return out
 

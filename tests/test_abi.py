@@ -49,8 +49,8 @@ def test_invalid_arguments_return_codes_without_a_gpu(built_lib):
     """Argument validation happens before any CUDA call, so it can be exercised on the CPU box."""
     built_lib.d3f_last_error.restype = ctypes.c_char_p
     built_lib.d3f_kpconv_forward.restype = ctypes.c_int
-    rc = built_lib.d3f_unary_forward(None, None, ctypes.c_int(-1), ctypes.c_int(4), ctypes.c_int(4), None, None, None,
-                                     None, ctypes.c_float(-1.0), None, None)
+    rc = built_lib.d3f_unary_forward(None, None, None, ctypes.c_int(-1), ctypes.c_int(4), ctypes.c_int(4), None, None,
+                                     None, None, ctypes.c_float(-1.0), None, None, None)
     assert rc == -1
     assert b"bad shape" in built_lib.d3f_last_error()
     built_lib.d3f_radius_neighbors_workspace_bytes.restype = ctypes.c_size_t

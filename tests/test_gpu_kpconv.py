@@ -248,3 +248,39 @@ def test_deformable_architecture_runs_and_matches(cuda):
     F_ref = ok.EncoderOracle(cfg, params, np.float64).encoder(inputs)
     for l, (a, b) in enumerate(zip(out["F"], F_ref)):
         assert rel_err(a.cpu().numpy(), b) < RTOL, "level %d" % l
+
+
+@pytest.mark.parametrize("Nq,Ns,H,Cout", [(6000, 6000, 40, 32), (4001, 9000, 37, 32), (20011, 20011, 45, 32),
+                                          (3600, 3600, 8, 32)])
+def test_kpconv_fused_kernel_matches_restatement_and_two_kernel_path(cuda, monkeypatch, Nq, Ns, H, Cout):
+    """The persistent fused kernel of the Cin = 32 layers (kpconv_fused.cu: gather + correlation on mma.sync, contraction
+    on tcgen05 out of a shared-memory A operand): vs the float64 restatement (1e-4) and vs the two-kernel path of the
+    same library (both 3xTF32: agree far below the tolerance). Ragged tail tile (Nq % 48 != 0), strided queries
+    (Nq != Ns), H not a multiple of 8, fused BN + LeakyReLU epilogue."""
+    from d3feat_b200 import convolution_ops as co
+    rng = np.random.default_rng(Nq + H)
+    q, s, idx, f, Kp, W = make_case(rng, Nq, Ns, H, 32, Cout, extent=0.05)
+    f[::5] = -np.abs(f[::5])                      # some supports do not count towards nn (:249-253)
+    args = [t(x, cuda) for x in (q, s, idx, f, Kp, W)]
+    scale = rng.uniform(0.5, 1.5, Cout).astype(np.float32)
+    shift = rng.normal(size=Cout).astype(np.float32)
+    epi = (t(scale, cuda), t(shift, cuda), 0.2)
+    monkeypatch.setenv("D3F_FUSED_KPCONV", "1")
+    co.packed_weight(args[5])                     # the one-time weight packing is not part of a call
+    n0 = co._lib.launch_count()
+    fused = co.KPConv_ops(*args, 0.05, "linear", "sum", epilogue=epi)
+    fused_raw = co.KPConv_ops(*args, 0.05, "linear", "sum")
+    launches_fused = co._lib.launch_count() - n0
+    monkeypatch.setenv("D3F_FUSED_KPCONV", "0")
+    n0 = co._lib.launch_count()
+    two = co.KPConv_ops(*args, 0.05, "linear", "sum", epilogue=epi)
+    assert launches_fused == 6      # per call: support packing, 8 KB-image weight packing, ONE persistent kernel
+    ref = ok.kpconv_ops(q, s, idx, f, Kp, W, 0.05, "linear", "sum", dtype=np.float64)
+    assert rel_err(fused_raw.cpu().numpy(), ref) < RTOL
+    y = ref * scale + shift
+    y = np.where(y > 0, y, 0.2 * y)
+    assert rel_err(fused.cpu().numpy(), y) < RTOL
+    assert rel_err(fused.cpu().numpy(), two.cpu().numpy()) < 2e-5
+    # bit-reproducible (no atomics, fixed tile schedule)
+    monkeypatch.setenv("D3F_FUSED_KPCONV", "1")
+    assert torch.equal(co.KPConv_ops(*args, 0.05, "linear", "sum", epilogue=epi), fused)

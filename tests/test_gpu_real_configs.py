@@ -288,3 +288,75 @@ def test_batch_pipeline_result_is_ordered_on_the_callers_stream(cuda):
     pipe.drain()
     for g in got:
         assert torch.equal(g, want)
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  the sync-free form: static pyramid + device-side row counts + CUDA graph replay (encoder.GraphPipeline)
+# ----------------------------------------------------------------------------------------------------------
+
+def test_static_pyramid_equals_exact_pyramid(cuda):
+    """d3f_pyramid_build, static form (no device->host read, capacity-sized launches, level sizes in device memory):
+    counts, points and every index matrix -- including the shadow index = the actual support count -- equal the exact
+    form's on the rows that exist."""
+    from d3feat_b200 import synth, pyramid as pyr
+    from d3feat_b200.encoder import KPFCNN
+    cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+    enc = KPFCNN(cfg, synth.make_params(cfg, 0), BENCH_LIMITS, device=cuda)
+    clouds = [synth.room_fragment(110, 9000), synth.room_fragment(111, 7000)]
+    P = np.concatenate(clouds, 0)
+    L = np.array([c.shape[0] for c in clouds], np.int32)
+    exact = enc.build_inputs(P, L)
+    sizes = [int(p.shape[0]) for p in exact["points"]]
+    bb = np.concatenate([P.min(0) - 0.1, P.max(0) + 0.1]).astype(np.float32)
+    buf = pyr.PyramidBuffers(cfg, BENCH_LIMITS, pyr.bucket_capacities(sizes, 1.2), 2, cuda, bbox=bb)
+    buf.points0[:P.shape[0]].copy_(t(P, cuda))
+    buf.lengths0.copy_(t(L, cuda))
+    buf.n0.fill_(P.shape[0])
+    st = enc.build_inputs_static(buf)
+    assert st["counts"][:5].cpu().tolist() == sizes and int(st["status"].item()) == 0
+    for l in range(5):
+        n = sizes[l]
+        assert st["points"][l].shape[0] == buf.caps[l] >= n
+        assert torch.equal(st["points"][l][:n], exact["points"][l])
+        assert torch.equal(st["lengths"][l], exact["lengths"][l])
+        assert torch.equal(st["neighbors"][l][:n], exact["neighbors"][l])
+        if l < 4:
+            assert torch.equal(st["pools"][l][:sizes[l + 1]], exact["pools"][l])
+            assert torch.equal(st["upsamples"][l][:n], exact["upsamples"][l])
+
+
+def test_graph_pipeline_matches_exact_path_and_flags_overflow(cuda):
+    """Five batches of different sizes through ONE captured bucket (3-slot ring, pyramid(i+1) || encoder(i)): every
+    result equals the one-batch-at-a-time exact path (the deep GEMMs may pick another deterministic split-K plan for the
+    capacity-sized launch, hence 2e-5 instead of bit equality), no host synchronisation is needed to get there, and a
+    batch that does not fit the bucket is reported through the status word."""
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN, GraphPipeline
+    cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+    enc = KPFCNN(cfg, synth.make_params(cfg, 5), [35, 33, 34, 36, 30], device=cuda)
+    batches = []
+    for i, n in enumerate([12000, 11000, 12000, 9500, 11800]):
+        clouds = [synth.room_fragment(120 + 2 * i, n), synth.room_fragment(121 + 2 * i, n - 700)]
+        batches.append((np.concatenate(clouds, 0), np.array([c.shape[0] for c in clouds], np.int32)))
+    want = [enc(P, L, decoder=False)["F"] for P, L in batches]
+    pipe = GraphPipeline.for_batch(enc, t(batches[0][0], cuda), t(batches[0][1], cuda), slack=1.2)
+    pipe.prime(t(batches[0][0], cuda), t(batches[0][1], cuda))
+    got = []
+    for i in range(len(batches)):
+        nxt = batches[i + 1] if i + 1 < len(batches) else None
+        res, counts = pipe.step(t(nxt[0], cuda), t(nxt[1], cuda)) if nxt else pipe.step()
+        got.append((res.clone(), counts.clone()))        # consumed on the caller's stream, no explicit sync
+    pipe.check()
+    assert pipe.kernels_per_step > 100
+    for i, ((res, counts), F) in enumerate(zip(got, want)):
+        n = int(counts[4].item())
+        assert n == F[-1].shape[0], i
+        assert rel_err(res[:n].cpu().numpy(), F[-1].cpu().numpy()) < 2e-5, i
+    # a batch with far more level-1 cells than the bucket was sized for: flagged, not silently truncated
+    rng = np.random.default_rng(0)
+    ext = pipe.bbox[3:] - pipe.bbox[:3]
+    spread = (pipe.bbox[:3] + 0.05 * ext + rng.uniform(0.0, 0.9, (batches[0][0].shape[0], 3)) * ext).astype(np.float32)
+    pipe.prime(t(spread, cuda), t(batches[0][1], cuda))
+    pipe.step()
+    with pytest.raises(RuntimeError):
+        pipe.check()
