@@ -360,3 +360,76 @@ def test_graph_pipeline_matches_exact_path_and_flags_overflow(cuda):
     pipe.step()
     with pytest.raises(RuntimeError):
         pipe.check()
+
+
+# ----------------------------------------------------------------------------------------------------------
+#  behavioural anchor of the TF-graph half on the GPU: the RELEASED model registers the reference's demo pair
+# ----------------------------------------------------------------------------------------------------------
+
+def test_released_model_registers_the_demo_pair_on_the_gpu(cuda):
+    """demo_registration.py:121-170 / utils/tester.py:198-229 with the CUDA path: the released 3DMatch snapshot
+    (weights, BN statistics, kernel points of results/Log_contraloss/snapshots/snap-54) on the reference's two demo
+    fragments, anchor || positive stacked like the reference's batch. (1) descriptors and detection scores of ALL
+    14 007 + 13 530 points agree with the float64 numpy restatement to 1e-4; (2) keypoints by score, mutual nearest
+    neighbours in descriptor space and RANSAC register the pair (same thresholds as the CPU test of the restatement).
+    The fixture (56 MB of released weights) is built by scripts/make_released_fixture.py into the git-ignored
+    tests/golden_local/; it travels to the GPU box with the snapshot."""
+    import os
+    from scipy.spatial import cKDTree
+    from d3feat_b200 import synth
+    from d3feat_b200.encoder import KPFCNN
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_local", "released_3dmatch_full.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden_local/released_3dmatch_full.npz not built (scripts/make_released_fixture.py)")
+    z = np.load(path)
+    params = {k[len("params|"):].replace("|", "/"): z[k] for k in z.files if k.startswith("params|")}
+    cfg = synth.Config(architecture=str(z["architecture"]).split(),
+                       first_subsampling_dl=float(z["cfg|first_subsampling_dl"]),
+                       density_parameter=float(z["cfg|density_parameter"]), KP_extent=float(z["cfg|KP_extent"]),
+                       first_features_dim=int(z["cfg|first_features_dim"]),
+                       num_kernel_points=int(z["cfg|num_kernel_points"]), in_features_dim=int(z["cfg|in_features_dim"]),
+                       KP_influence=str(z["cfg|KP_influence"]), convolution_mode=str(z["cfg|convolution_mode"]))
+    clouds = [z["cloud0"], z["cloud1"]]
+    assert [c.shape[0] for c in clouds] == [14007, 13530]
+    limits = [37, 35, 36, 38, 38]                 # calibrate_neighbors on the pair (tests/golden/released_demo_summary.json)
+    P = np.concatenate(clouds, 0)
+    L = np.array([c.shape[0] for c in clouds], np.int32)
+    out = KPFCNN(cfg, params, limits, device=cuda)(P, L)
+    desc, score = out["descriptors"].cpu().numpy(), out["scores"].cpu().numpy()
+    assert desc.shape == (P.shape[0], 32) and score.shape == (P.shape[0], 1)
+    # (1) every point vs the float64 restatement on the same pyramid
+    inputs = _inputs_to_numpy(out, P.shape[0])
+    orc = ok.EncoderOracle(cfg, params, np.float64)
+    d_ref, s_ref = orc.decoder(inputs, orc.encoder(inputs), return_scores=True)
+    assert np.abs(desc - d_ref).max() < RTOL      # unit-norm rows
+    assert rel_err(score, s_ref) < RTOL
+    # (2) the demo_registration flow
+    n0 = clouds[0].shape[0]
+    d = [desc[:n0], desc[n0:]]
+    s = [score[:n0, 0], score[n0:, 0]]
+    kp = [np.argsort(x)[-1500:] for x in s]
+    d0, d1 = d[0][kp[0]], d[1][kp[1]]
+    nn01 = cKDTree(d1).query(d0)[1]
+    mutual = np.nonzero(cKDTree(d0).query(d1)[1][nn01] == np.arange(d0.shape[0]))[0]
+    src, dst = clouds[0][kp[0]][mutual], clouds[1][kp[1]][nn01[mutual]]
+
+    def kabsch(a, b):
+        ca, cb = a.mean(0), b.mean(0)
+        u, _, vt = np.linalg.svd((a - ca).T @ (b - cb))
+        sgn = np.sign(np.linalg.det(vt.T @ u.T))
+        r = vt.T @ np.diag([1, 1, sgn]) @ u.T
+        return r, cb - r @ ca
+    rng = np.random.default_rng(0)
+    best = (0, np.eye(3), np.zeros(3))
+    for _ in range(3000):
+        i = rng.choice(src.shape[0], 3, replace=False)
+        r, tt = kabsch(src[i], dst[i])
+        inl = int(np.sum(np.linalg.norm(src @ r.T + tt - dst, axis=1) < 0.05))
+        if inl > best[0]:
+            best = (inl, r, tt)
+    inl = np.linalg.norm(src @ best[1].T + best[2] - dst, axis=1) < 0.05
+    r, tt = kabsch(src[inl], dst[inl])
+    assert mutual.size > 100 and inl.sum() / mutual.size > 0.3
+    before = np.mean(cKDTree(clouds[1]).query(clouds[0])[0] < 0.05)
+    after = np.mean(cKDTree(clouds[1]).query(clouds[0] @ r.T + tt)[0] < 0.05)
+    assert before < 0.15 and after > 0.6
