@@ -286,7 +286,7 @@ size_t grid_subsample_workspace_bytes(int N, int B) {
 int grid_subsample(const float* pts, const int* batch_len, int B, int N, float dl, const float* feats, int fdim,
                    const int* classes, int ldim, const float* host_bbox, float* out_pts, float* out_feats,
                    int* out_classes, int* out_batch_len, int* out_M, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream, const int* n_dev, int out_capacity, int* status) {
+                   cudaStream_t stream, const int* n_dev, int out_capacity, int* status, const int* start_pre) {
   if (out_capacity < 0) out_capacity = N;   // a subsampled cloud never has more points than its parent
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "grid_subsample: B=%d must be in [1,%d]", B, kMaxBatch);
   D3F_REQUIRE(N >= 0 && dl > 0.f, D3F_ERR_INVALID, "grid_subsample: N=%d, dl=%g invalid", N, (double)dl);
@@ -309,7 +309,8 @@ int grid_subsample(const float* pts, const int* batch_len, int B, int N, float d
   D3F_REQUIRE(cell_bits + 1 + bbits <= 62, D3F_ERR_CAPACITY,
               "grid_subsample: grid of 2^%d cells x %d clouds exceeds the 62-bit sort key", cell_bits, B);
 
-  if (launch_batch_start(batch_len, B, w.start, stream)) return D3F_ERR_CUDA;
+  if (start_pre != nullptr) w.start = const_cast<int*>(start_pre);   // the caller already scanned these lengths
+  else if (launch_batch_start(batch_len, B, w.start, stream)) return D3F_ERR_CUDA;
   D3F_CUDA(cudaMemsetAsync(w.err, 0, sizeof(int), stream));
   // per-cloud bbox: min slots 0xFFFFFFFF, max slots 0
   D3F_CUDA(cudaMemsetAsync(w.bbox_ord, 0, sizeof(unsigned) * 6 * B, stream));

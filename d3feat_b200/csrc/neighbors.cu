@@ -115,7 +115,7 @@ size_t radius_neighbors_workspace_bytes(int Ns, int B, float radius, const float
 
 int radius_neighbors_build(const float* supports, const int* s_batch_len, int B, int Ns, float radius,
                            const float* host_bbox, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                           const int* ns_dev) {
+                           const int* ns_dev, const int* s_start_pre) {
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch, D3F_ERR_INVALID, "radius_neighbors: B=%d must be in [1,%d]", B, kMaxBatch);
   D3F_REQUIRE(radius > 0.f && Ns >= 0 && host_bbox != nullptr, D3F_ERR_INVALID,
               "radius_neighbors: radius=%g Ns=%d invalid or host_bbox missing", (double)radius, Ns);
@@ -129,7 +129,8 @@ int radius_neighbors_build(const float* supports, const int* s_batch_len, int B,
   Carver cv(workspace, workspace_bytes);
   NbWs w;
   carve_nb(cv, Ns, B, total, w);
-  if (launch_batch_start(s_batch_len, B, w.s_start, stream)) return D3F_ERR_CUDA;
+  if (s_start_pre != nullptr) w.s_start = const_cast<int*>(s_start_pre);   // the caller already scanned these lengths
+  else if (launch_batch_start(s_batch_len, B, w.s_start, stream)) return D3F_ERR_CUDA;
   D3F_CUDA(cudaMemsetAsync(w.cell_cnt, 0, sizeof(int) * ((size_t)total + 1), stream));
   if (Ns == 0) {
     D3F_CUDA(cudaMemsetAsync(w.cell_start, 0, sizeof(int) * ((size_t)total + 1), stream));
@@ -367,7 +368,7 @@ radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restri
 static int query_common(bool fill, const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                         const float* host_bbox, const void* workspace, int cols, int pad_value, int* counts,
                         int* out_max, int* out_idx, cudaStream_t stream, const int* nq_dev = nullptr,
-                        const int* pad_dev = nullptr) {
+                        const int* pad_dev = nullptr, const int* q_start_pre = nullptr) {
   D3F_REQUIRE(B >= 1 && B <= kMaxBatch && Nq >= 0 && radius > 0.f && host_bbox != nullptr, D3F_ERR_INVALID,
               "radius_neighbors: invalid arguments (B=%d Nq=%d radius=%g)", B, Nq, (double)radius);
   NbGrid g = make_grid(host_bbox, radius);
@@ -376,7 +377,8 @@ static int query_common(bool fill, const float* queries, const int* q_batch_len,
   Carver cv(const_cast<void*>(workspace), ~(size_t)0);
   NbWs w;
   carve_nb(cv, Ns, B, total, w);
-  if (launch_batch_start(q_batch_len, B, w.q_start, stream)) return D3F_ERR_CUDA;
+  if (q_start_pre != nullptr) w.q_start = const_cast<int*>(q_start_pre);
+  else if (launch_batch_start(q_batch_len, B, w.q_start, stream)) return D3F_ERR_CUDA;
   if (out_max != nullptr && !fill) D3F_CUDA(cudaMemsetAsync(out_max, 0, sizeof(int), stream));
   if (Nq == 0) return D3F_OK;
   float r2 = radius * radius;  // neighbors.cpp:226 (fp32 product)
@@ -404,12 +406,12 @@ int radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq,
 
 int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                           const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
-                          cudaStream_t stream, const int* nq_dev, const int* pad_dev) {
+                          cudaStream_t stream, const int* nq_dev, const int* pad_dev, const int* q_start_pre) {
   D3F_REQUIRE(cols >= 0 && (out_idx != nullptr || cols == 0 || Nq == 0), D3F_ERR_INVALID,
               "radius_neighbors_fill: cols=%d / null output", cols);
   if (cols == 0) return D3F_OK;
   return query_common(true, queries, q_batch_len, Nq, B, Ns, radius, host_bbox, workspace, cols, pad_value, nullptr,
-                      nullptr, out_idx, stream, nq_dev, pad_dev);
+                      nullptr, out_idx, stream, nq_dev, pad_dev, q_start_pre);
 }
 
 }  // namespace d3f

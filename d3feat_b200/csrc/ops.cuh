@@ -35,14 +35,15 @@ size_t grid_subsample_workspace_bytes(int N, int B);
 int grid_subsample(const float* pts, const int* batch_len, int B, int N, float dl, const float* feats, int fdim,
                    const int* classes, int ldim, const float* host_bbox, float* out_pts, float* out_feats,
                    int* out_classes, int* out_batch_len, int* out_M, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream, const int* n_dev = nullptr, int out_capacity = -1, int* status = nullptr);
+                   cudaStream_t stream, const int* n_dev = nullptr, int out_capacity = -1, int* status = nullptr,
+                   const int* start_pre = nullptr);
 
 // ---- neighbors.cu -----------------------------------------------------------------------------------
 size_t radius_neighbors_workspace_bytes(int Ns, int B, float radius, const float* host_bbox);
 // ns_dev / nq_dev / pad_dev (optional): actual row counts / the shadow index in device memory; Ns / Nq are then capacities
 int radius_neighbors_build(const float* supports, const int* s_batch_len, int B, int Ns, float radius,
                            const float* host_bbox, void* workspace, size_t workspace_bytes, cudaStream_t stream,
-                           const int* ns_dev = nullptr);
+                           const int* ns_dev = nullptr, const int* s_start_pre = nullptr);
 int radius_neighbors_count(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                            const float* host_bbox, const void* workspace, int* counts, int* out_max,
                            cudaStream_t stream);
@@ -50,7 +51,8 @@ int radius_neighbors_order(const void* workspace, int Ns, int B, float radius, c
                            cudaStream_t stream);
 int radius_neighbors_fill(const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                           const float* host_bbox, const void* workspace, int cols, int pad_value, int* out_idx,
-                          cudaStream_t stream, const int* nq_dev = nullptr, const int* pad_dev = nullptr);
+                          cudaStream_t stream, const int* nq_dev = nullptr, const int* pad_dev = nullptr,
+                          const int* q_start_pre = nullptr);
 
 // ---- pyramid.cu -------------------------------------------------------------------------------------
 size_t pyramid_workspace_bytes(int B, const d3f_pyramid_spec* spec, const int* capacity, const float* host_bbox);

@@ -32,44 +32,47 @@ __global__ void __launch_bounds__(256) colmin_kernel(const float* __restrict__ x
   }
 }
 
-// one warp per pooled row; lanes stride the channels (float4 when C % 4 == 0)
+// one warp per (pooled row, 128-channel slab): lanes own 4 consecutive channels (float4 when C % 4 == 0). Splitting the
+// channels over warps matters at the deep levels (1204 rows x 1024 channels: one warp per row walked 8 slabs x 40
+// dependent row loads; now 8 warps walk 40 each)
 template <int VEC>
 __global__ void __launch_bounds__(256)
 ind_max_pool_kernel(const float* __restrict__ x, const int* __restrict__ inds, int N1cap, int N2cap,
-                    const int* __restrict__ n1_dev, const int* __restrict__ n2_dev, int H, int C,
+                    const int* __restrict__ n1_dev, const int* __restrict__ n2_dev, int H, int C, int slabs,
                     unsigned* __restrict__ colmin_ord, float* __restrict__ out) {
   const int N1 = dyn_rows(N1cap, n1_dev), N2 = dyn_rows(N2cap, n2_dev);
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int warp = gw / slabs, slab = gw - warp * slabs;
   if (warp >= N2) return;
   const int* row = inds + (size_t)warp * H;
-  for (int c0 = lane * VEC; c0 < C; c0 += 32 * VEC) {
-    float best[VEC];
+  const int c0 = slab * 32 * VEC + lane * VEC;
+  if (c0 >= C) return;
+  float best[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) best[v] = -3.402823466e38f;
-    bool any_real = false;
-    for (int h = 0; h < H; ++h) {
-      int id = row[h];
-      if (id < 0 || id >= N1) continue;
-      any_real = true;
-      const float* p = x + (size_t)id * C + c0;
-      if (VEC == 4) {
-        float4 t = *reinterpret_cast<const float4*>(p);
-        best[0] = fmaxf(best[0], t.x); best[1 % VEC] = fmaxf(best[1 % VEC], t.y);
-        best[2 % VEC] = fmaxf(best[2 % VEC], t.z); best[3 % VEC] = fmaxf(best[3 % VEC], t.w);
-      } else {
-        best[0] = fmaxf(best[0], *p);
-      }
-    }
-    if (!any_real) {   // every neighbour is the shadow: the row is the column minimum, filled in by the fix-up pass
-      if (lane == 0 && c0 == 0) colmin_ord[C] = 0u;
-      continue;
-    }
+  for (int v = 0; v < VEC; ++v) best[v] = -3.402823466e38f;
+  bool any_real = false;
+  for (int h = 0; h < H; ++h) {
+    int id = row[h];
+    if (id < 0 || id >= N1) continue;
+    any_real = true;
+    const float* p = x + (size_t)id * C + c0;
     if (VEC == 4) {
-      *reinterpret_cast<float4*>(out + (size_t)warp * C + c0) =
-          make_float4(best[0], best[1 % VEC], best[2 % VEC], best[3 % VEC]);
+      float4 t = *reinterpret_cast<const float4*>(p);
+      best[0] = fmaxf(best[0], t.x); best[1 % VEC] = fmaxf(best[1 % VEC], t.y);
+      best[2 % VEC] = fmaxf(best[2 % VEC], t.z); best[3 % VEC] = fmaxf(best[3 % VEC], t.w);
     } else {
-      out[(size_t)warp * C + c0] = best[0];
+      best[0] = fmaxf(best[0], *p);
     }
+  }
+  if (!any_real) {   // every neighbour is the shadow: the row is the column minimum, filled in by the fix-up pass
+    if (lane == 0 && slab == 0) colmin_ord[C] = 0u;
+    return;
+  }
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(out + (size_t)warp * C + c0) =
+        make_float4(best[0], best[1 % VEC], best[2 % VEC], best[3 % VEC]);
+  } else {
+    out[(size_t)warp * C + c0] = best[0];
   }
 }
 
@@ -103,8 +106,11 @@ int ind_max_pool(const float* x, const int* inds, int N1, int N2, int H, int C, 
   D3F_CUDA(cudaMemsetAsync(colmin, 0xff, sizeof(unsigned) * ((size_t)C + 1), stream));
   int blocks = ceil_div(N2 * 32, 256);
   bool v4 = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (v4) ind_max_pool_kernel<4><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, H, C, colmin, out);
-  else ind_max_pool_kernel<1><<<blocks, 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, H, C, colmin, out);
+  const int slabs = ceil_div(C, v4 ? 128 : 32);
+  const long long pool_blocks = ((long long)N2 * slabs * 32 + 255) / 256;
+  D3F_REQUIRE(pool_blocks < (1ll << 31), D3F_ERR_CAPACITY, "ind_max_pool: %d rows x %d channels exceed the launch grid", N2, C);
+  if (v4) ind_max_pool_kernel<4><<<(unsigned)pool_blocks, 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, H, C, slabs, colmin, out);
+  else ind_max_pool_kernel<1><<<(unsigned)pool_blocks, 256, 0, stream>>>(x, inds, N1, N2, n1_dev, n2_dev, H, C, slabs, colmin, out);
   D3F_LAUNCH_CHECK("ind_max_pool_kernel");
   dim3 grid(ceil_div(C, 32), min(ceil_div(N1, 64), 4 * kNumSMs));
   colmin_kernel<<<grid, 256, 0, stream>>>(x, N1, n1_dev, C, colmin);

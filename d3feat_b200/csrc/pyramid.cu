@@ -36,6 +36,7 @@ size_t pyramid_workspace_bytes(int B, const d3f_pyramid_spec* spec, const int* c
   int L = spec->n_levels;
   if (L < 1 || L > D3F_MAX_LEVELS) return 0;
   size_t total = align_up(grid_subsample_workspace_bytes(capacity[0], B) + 512, 256);
+  total += align_up(sizeof(int) * (size_t)D3F_MAX_LEVELS * (B + 1), 256);   // exclusive scans of every level's lengths
   for (int l = 0; l < L; ++l) {
     float radii[3] = {spec->conv_radius[l], spec->sub_dl[l] > 0.f ? spec->pool_radius[l] : -1.f,
                       (l > 0 && spec->sub_dl[l - 1] > 0.f) ? spec->up_radius[l - 1] : -1.f};
@@ -87,6 +88,11 @@ int pyramid_build(const float* points, const int* lengths, int B, int N0, const 
   void* sub_ws = base;
   size_t sub_bytes = align_up(grid_subsample_workspace_bytes(capacity[0], B) + 512, 256);
   off += sub_bytes;
+  // start[l][b] = first row of cloud b at level l: scanned ONCE per level (every grid build, search and subsampling
+  // of that level used to launch its own scan: 22 launches per step instead of 5)
+  int* starts = (int*)(base + off);
+  off += align_up(sizeof(int) * (size_t)D3F_MAX_LEVELS * (B + 1), 256);
+  if (launch_batch_start(lengths, B, starts, stream)) return D3F_ERR_CUDA;
   // level counts live in the caller's buffer, or (exact form without one) in the tail of the subsampling region
   int* counts = d_counts != nullptr ? d_counts : (int*)((char*)sub_ws + sub_bytes - 256);
   int* status = d_status != nullptr ? d_status : counts + D3F_MAX_LEVELS;
@@ -118,7 +124,7 @@ int pyramid_build(const float* points, const int* lengths, int B, int N0, const 
     off += g.bytes;
     D3F_REQUIRE(off <= workspace_bytes, D3F_ERR_WORKSPACE, "pyramid_build: workspace exhausted");
     int rc = radius_neighbors_build(lvl_pts[l], lvl_len[l], B, lvl_n[l], radius, host_bbox, g.ws, g.bytes, stream,
-                                    counts + l);
+                                    counts + l, starts + (size_t)l * (B + 1));
     if (rc) return rc;
     ++n_slots;
     *out = &g;
@@ -127,7 +133,7 @@ int pyramid_build(const float* points, const int* lengths, int B, int N0, const 
   // the workspace of a grid is carved with the CAPACITY of its level (the query side re-derives the same layout)
   auto fill = [&](int lq, int ls, GridSlot* g, int lim, int* out) -> int {
     return radius_neighbors_fill(lvl_pts[lq], lvl_len[lq], lvl_n[lq], B, lvl_n[ls], g->radius, host_bbox, g->ws, lim,
-                                 lvl_n[ls], out, stream, counts + lq, counts + ls);
+                                 lvl_n[ls], out, stream, counts + lq, counts + ls, starts + (size_t)lq * (B + 1));
   };
 
   for (int l = 0; l < L; ++l) {
@@ -147,8 +153,9 @@ int pyramid_build(const float* points, const int* lengths, int B, int N0, const 
       int* d_M = counts + l + 1;
       int rc = grid_subsample(lvl_pts[l], lvl_len[l], B, lvl_n[l], spec->sub_dl[l], nullptr, 0, nullptr, 0, host_bbox,
                               out_points[l + 1], nullptr, nullptr, out_lengths[l + 1], d_M, sub_ws, sub_bytes - 256,
-                              stream, counts + l, capacity[l + 1], status);
+                              stream, counts + l, capacity[l + 1], status, starts + (size_t)l * (B + 1));
       if (rc) return rc;
+      if (launch_batch_start(out_lengths[l + 1], B, starts + (size_t)(l + 1) * (B + 1), stream)) return D3F_ERR_CUDA;
       int M = capacity[l + 1];
       if (exact) {
         D3F_CUDA(cudaMemcpyAsync(&M, d_M, sizeof(int), cudaMemcpyDeviceToHost, stream));

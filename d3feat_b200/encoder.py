@@ -193,16 +193,22 @@ class GraphPipeline:
     (rows beyond counts[-1] are undefined); both stay valid until the slot is reused DEPTH steps later. Mirrors the
     overlap the reference gets from tf.data prefetch (datasets/common.py:744-763)."""
 
-    DEPTH = 3
+    DEPTH = 4
 
-    def __init__(self, enc, capacities, n_clouds, bbox, decoder=False, post=None):
+    def __init__(self, enc, capacities, n_clouds, bbox, decoder=False, post=None, encoder_streams=2):
         self.enc, self.decoder, self.post = enc, decoder, post
         dev = enc.device
         self.caps = [int(c) for c in capacities]
         self.n_clouds = int(n_clouds)
         self.bbox = np.ascontiguousarray(bbox, np.float32)
         self.s_pyr = torch.cuda.Stream(device=dev)
-        self.s_enc = torch.cuda.Stream(device=dev)
+        # Encoders of consecutive batches alternate between `encoder_streams` streams: the deep pyramid levels (a few
+        # thousand rows) cannot fill 148 SMs on their own, so the tail of encoder(i) runs under the level-0 kernels of
+        # encoder(i + 1). Results still come back in batch order (each step waits for its own batch's event).
+        self.s_encs = [torch.cuda.Stream(device=dev) for _ in range(max(1, int(encoder_streams)))]
+        self.s_enc = self.s_encs[0]
+        self.n_stepped = 0
+        self.DEPTH = len(self.s_encs) + 2     # encoders in flight + the pyramid being built + one slot of slack
         self.slots = [pyramid.PyramidBuffers(enc.config, enc.limits, self.caps, self.n_clouds, dev, bbox=self.bbox)
                       for _ in range(self.DEPTH)]
         self.g_pyr = [None] * self.DEPTH
@@ -300,15 +306,18 @@ class GraphPipeline:
         cur = torch.cuda.current_stream(self.enc.device)
         inputs_ready = self._mark_inputs() if next_points is not None else None
         inputs, F, res = self.out[k]
-        with torch.cuda.stream(self.s_enc):
-            self.s_enc.wait_event(self.ready[k])
+        s_enc = self.s_encs[self.n_stepped % len(self.s_encs)]
+        self.n_stepped += 1
+        self.s_enc = s_enc                    # the stream this step's result is produced on
+        with torch.cuda.stream(s_enc):
+            s_enc.wait_event(self.ready[k])
             if pre is not None:
                 pre()
             self.g_enc[k].replay()
             if self.post is not None:
                 res = self.post(inputs, res)
             ev = torch.cuda.Event()
-            ev.record(self.s_enc)
+            ev.record(s_enc)
             self.done[k] = ev
         cur.wait_event(ev)
         self.pending = self._load(next_points, next_lengths, inputs_ready) if next_points is not None else None
@@ -316,7 +325,8 @@ class GraphPipeline:
 
     def drain(self):
         self.s_pyr.synchronize()
-        self.s_enc.synchronize()
+        for s in self.s_encs:
+            s.synchronize()
 
     def check(self):
         """Raise if any replayed batch overflowed the bucket (synchronises)."""
