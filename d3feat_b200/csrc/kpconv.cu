@@ -7,6 +7,8 @@
 // in registers. Stage 2 is the dense contraction  out[n,:] = (sum_k wf[n,k,:] @ W[k]) / nn[n]  ==
 // [Nq, K*Cin] @ [K*Cin, Cout] with the block epilogue fused (gemm.cu). The [N,H,K,3], [N,H,K], [N,H,Cin]
 // intermediates of the TF graph are never materialised; wf is produced in query chunks that stay in L2.
+#include <stdlib.h>
+
 #include "ops.cuh"
 
 namespace d3f {
@@ -250,10 +252,12 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-// MUFU.SQRT: one instruction instead of the ~10-instruction IEEE sequence (max error ~1 ulp; tolerance 1e-4)
+// MUFU.SQRT: one instruction instead of the ~10-instruction IEEE sequence (max error ~1 ulp; tolerance 1e-4). The
+// .ftz form matters: without it ptxas wraps the MUFU in a denormal rescue (FSETP + FMUL 2^24 + FMUL 2^-12, four
+// instructions per root); every argument here is d^2 + 1e-10 >= 1e-10, never subnormal.
 __device__ __forceinline__ float sqrt_approx(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 
@@ -416,6 +420,112 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], 
 __device__ __forceinline__ void split3(float x, unsigned& hi, unsigned& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
   lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The same stage 1 with the instruction stream pared down for the configuration every D3Feat model runs (rigid, linear
+// influence, sum aggregation). ncu (profiles/r2_all_kernels_ncu.txt) shows the general kernel issue
+// bound at 63 % with ~190 instructions per 8-neighbour step, of which barely 90 are the correlation / split / MMA
+// work. What is removed here:
+//  * the shadow test on the weights: the rigid shadow point sits at 1e6 (:190), its linear influence is
+//    max(1 - ~1e7, 0) = 0 on its own; the same trick parks the 16th (non-existent) kernel point of lanes g = 7 at 1e6;
+//  * the ballot / popc chain of the neighbour count: every lane counts its own two neighbours, lanes 0-3 are reduced
+//    with two shuffles at the end;
+//  * the per-step re-derivation of the feature base pointer (ptxas rematerialised it from %tid every step: nine
+//    instructions per row load) -- the pointer is made opaque and rows are addressed with one IMAD.WIDE;
+//  * the epsilon add (folded into the first FMA of d^2), 64-bit index arithmetic (rows are addressed with 32-bit
+//    element offsets; the host routes layers beyond 2^31 elements to the general kernel).
+// (cvt.rna.tf32.f32 would be the natural split, but ptxas expands it to four instructions with an Inf/NaN guard; the
+//  integer add-and-mask of split3 is two)
+
+template <int NT>
+__global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_fast_kernel(Stage1Params p) {
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
+  constexpr int K = 15;
+  static_assert(NT % 4 == 0, "one float4 per four n-tiles");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = p.n0 + blockIdx.x * kS1Warps + warp;
+  if (n >= n1_) return;  // warp-uniform
+  const int kA = g, kB = g + 8;
+  const bool validB = kB < K;
+  const float kax = p.Kp[3 * kA], kay = p.Kp[3 * kA + 1], kaz = p.Kp[3 * kA + 2];
+  const float kbx = validB ? p.Kp[3 * kB] : 1e6f, kby = validB ? p.Kp[3 * kB + 1] : 1e6f,
+              kbz = validB ? p.Kp[3 * kB + 2] : 1e6f;
+  const int qid = p.order ? p.order[n] : n;
+  const float qx = p.q[3 * (size_t)qid], qy = p.q[3 * (size_t)qid + 1], qz = p.q[3 * (size_t)qid + 2];
+  const int* row = p.idx + (size_t)qid * p.H + t;
+  const float inv_scale = p.inv_scale;
+  const unsigned Ns = (unsigned)Ns_;
+  const unsigned Cin = (unsigned)p.Cin;
+  int cnt = 0;
+
+  constexpr int CCH = NT * 8;   // channels per pass
+  for (int c0 = 0; c0 < p.Cin; c0 += CCH) {
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    const float* fcol = p.feat + c0 + NT * g;
+    asm volatile("" : "+l"(fcol));   // opaque: keep the pointer in registers instead of re-deriving it every step
+
+    for (int h0 = 0; h0 < p.H; h0 += 8) {
+      unsigned ida = Ns, idb = Ns;
+      if (h0 + t < p.H) ida = (unsigned)__ldg(row + h0);
+      if (h0 + t + 4 < p.H) idb = (unsigned)__ldg(row + h0 + 4);
+      ida = min(ida, Ns);       // -1 padding of the non-batch op (0xffffffff) behaves like the shadow
+      idb = min(idb, Ns);
+      const float4 spa = __ldg(&p.s4[ida]), spb = __ldg(&p.s4[idb]);
+      float fa[NT], fb[NT];
+#pragma unroll
+      for (int v = 0; v < NT; v += 4) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ida < Ns) x = __ldg(reinterpret_cast<const float4*>(fcol + (size_t)(ida * Cin) + v));
+        if (idb < Ns) y = __ldg(reinterpret_cast<const float4*>(fcol + (size_t)(idb * Cin) + v));
+        fa[v] = x.x; fa[v + 1] = x.y; fa[v + 2] = x.z; fa[v + 3] = x.w;
+        fb[v] = y.x; fb[v + 1] = y.y; fb[v + 2] = y.z; fb[v + 3] = y.w;
+      }
+      if (c0 == 0) cnt += (spa.w > 0.f ? 1 : 0) + (spb.w > 0.f ? 1 : 0);
+      const float rax = spa.x - qx, ray = spa.y - qy, raz = spa.z - qz;
+      const float rbx = spb.x - qx, rby = spb.y - qy, rbz = spb.z - qz;
+      auto weight = [&](float rx, float ry, float rz, float kx, float ky, float kz) {
+        const float dx = rx - kx, dy = ry - ky, dz = rz - kz;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1e-10f)));     // d^2 + 1e-10 (:215)
+        return fmaxf(fmaf(-sqrt_approx(d2), inv_scale, 1.f), 0.f);             // 1 - d / (2 extent), clipped
+      };
+      unsigned ah[4], al[4];
+      split3(weight(rax, ray, raz, kax, kay, kaz), ah[0], al[0]);
+      split3(weight(rax, ray, raz, kbx, kby, kbz), ah[1], al[1]);
+      split3(weight(rbx, rby, rbz, kax, kay, kaz), ah[2], al[2]);
+      split3(weight(rbx, rby, rbz, kbx, kby, kbz), ah[3], al[3]);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        unsigned bh0, bl0, bh1, bl1;
+        split3(fa[i], bh0, bl0);
+        split3(fb[i], bh1, bl1);
+        mma_tf32(acc[i], ah, bh0, bh1);
+        mma_tf32(acc[i], al, bh0, bh1);
+        mma_tf32(acc[i], ah, bl0, bl1);
+      }
+    }
+
+    // ---- write wf: rows kA (acc[.][0..1]) and kB (acc[.][2..3]), channels c0 + 2*NT*t + [0, 2*NT) -------------
+    float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c0 + 2 * NT * t;
+#pragma unroll
+    for (int v = 0; v < NT; v += 4) {
+      *reinterpret_cast<float4*>(dst + (size_t)kA * p.Cin + v) = make_float4(acc[v][0], acc[v + 1][0], acc[v + 2][0], acc[v + 3][0]);
+      *reinterpret_cast<float4*>(dst + (size_t)kA * p.Cin + NT + v) = make_float4(acc[v][1], acc[v + 1][1], acc[v + 2][1], acc[v + 3][1]);
+      if (validB) {
+        *reinterpret_cast<float4*>(dst + (size_t)kB * p.Cin + v) = make_float4(acc[v][2], acc[v + 1][2], acc[v + 2][2], acc[v + 3][2]);
+        *reinterpret_cast<float4*>(dst + (size_t)kB * p.Cin + NT + v) = make_float4(acc[v][3], acc[v + 1][3], acc[v + 2][3], acc[v + 3][3]);
+      }
+    }
+  }
+  if (p.inv_nn != nullptr) {
+    // lanes 0-3 (g == 0) hold the counts of the neighbour slots t, t+4 (mod 8) of every step: together all of them
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    if (lane == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(cnt, 1);
+  }
 }
 
 // FAST = the D3Feat configuration (KP_influence = linear, aggregation = sum) resolved at compile time; the
@@ -640,6 +750,14 @@ static int launch_stage1(int K, const Stage1Params& p, cudaStream_t stream) {
   if (K == 15 && al16 && (p.Cin == 32 || p.Cin == 64 || p.Cin % 128 == 0)) {
     const int blocks = ceil_div(nq, kS1Warps);
     const bool fast = p.influence == D3F_INFLUENCE_LINEAR && !p.closest;
+    static const bool no_pared = [] { const char* v = getenv("D3F_S1_PARED"); return v != nullptr && v[0] == '0'; }();
+    if (fast && !DEFORM && !no_pared && (long long)(p.Ns + 1) * p.Cin < (1ll << 31)) {
+      if (p.Cin == 32) kpconv_stage1_fast_kernel<4><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else if (p.Cin == 64) kpconv_stage1_fast_kernel<8><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else kpconv_stage1_fast_kernel<16><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      D3F_LAUNCH_CHECK("kpconv_stage1_fast_kernel");
+      return D3F_OK;
+    }
     if (fast) {
       if (p.Cin == 32) kpconv_stage1_mma_kernel<4, DEFORM, true><<<blocks, kS1Warps * 32, 0, stream>>>(p);
       else if (p.Cin == 64) kpconv_stage1_mma_kernel<8, DEFORM, true><<<blocks, kS1Warps * 32, 0, stream>>>(p);
@@ -795,13 +913,24 @@ static AuxStream* aux_stream() {
   return &a;
 }
 
-// queries per chunk: keep the wf chunk (K*Cin floats per query) around 40 MB (two buffers in flight) so it is produced and
-// consumed out of the 126 MB L2 instead of HBM
+// Queries per chunk of the two-kernel path (stage 1 writes wf[chunk, K*Cin], the contraction of chunk i overlaps
+// stage 1 of chunk i+1). Measured on B200 (profiles/r2_notes.md, 8 x 30k fragments, warm):
+//     rows per chunk       32->32 @ 240k   64->64 @ 60k   128->128 @ 15k
+//     40 MB of wf (r1)        0.60 ms         0.40 ms         0.20 ms
+//     37 888                  0.60            0.27            0.16
+//     75 776 / 120 064        0.56 / 0.57     0.26            0.16
+//     the whole layer         0.54            0.26            0.16
+// Keeping a chunk inside the 126 MB L2 is NOT what matters: every chunk costs a stage-1 tail, a GEMM launch with its
+// fixed latency and a partial wave, and both kernels fill the machine on their own so the overlap buys little, while
+// HBM takes the 460 MB wf round trip of the largest layer in well under the stage-1 time. So: one chunk per layer
+// up to 512 MB of wf per buffer (1 GB of scratch per encoder stream out of 180 GB); larger layers are cut into
+// equal chunks of that size.
 static int chunk_queries(int K, int Cin) {
-  long long per = (long long)K * Cin * 4;
-  long long n = (40ll << 20) / per;
+  static const int forced = [] { const char* v = getenv("D3F_KPCONV_CHUNK"); return v ? atoi(v) : 0; }();
+  if (forced >= 128) return forced / 128 * 128;      // tuning experiments
+  const long long per = (long long)K * Cin * 4;
+  long long n = (512ll << 20) / per;
   if (n < 1024) n = 1024;
-  if (n > (1 << 20)) n = 1 << 20;
   return (int)(n / 128 * 128);
 }
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ void split_hl(float x, unsigned& hi, unsigned& lo) {
 }
 __device__ __forceinline__ float sqrt_apx(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));   // .ftz: no denormal rescue around the MUFU
   return r;
 }
 

@@ -3,6 +3,11 @@ launches, total / share of the device time, DRAM bytes and achieved GB/s, tensor
 Optionally writes profiles/r2_traffic.json (DRAM bytes per launch of the dominant kernels, read by bench.py).
 
     python scripts/ncu_summarize.py gpurun_out/<run>/all_kernels.csv [--traffic profiles/r2_traffic.json]
+    python scripts/ncu_summarize.py gpurun_out/<run>/kpconv_op.csv --op kpconv_32_32 --iters 3 --traffic profiles/r2_traffic.json
+
+The second form is for a log of ONE operator repeated `--iters` times (scripts/ncu_targets.py with ONLY=kpconv): the
+DRAM bytes of every launch are summed and divided by the repetitions, and stored under the key bench.py looks up
+(`kpconv_<Cin>_<Cout>`: all kernels of one d3f_kpconv_forward call), merged into an existing traffic file.
 """
 import collections
 import csv
@@ -60,6 +65,16 @@ def main():
             f["l2bytes"] / t / 1e9, f["tensor"] / t, f["issue"] / t, f["warps"] / t, f["l2hit"] / t))
         traffic[name] = dict(dram_bytes_per_launch=(f["rd"] + f["wr"]) / f["n"], launches=int(f["n"]),
                              source="ncu dram__bytes_read.sum + dram__bytes_write.sum, " + path)
+    if "--op" in sys.argv:
+        import os
+        key = sys.argv[sys.argv.index("--op") + 1]
+        iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 1
+        tot = sum(f["rd"] + f["wr"] for f in fam.values()) / iters
+        n = sum(f["n"] for f in fam.values()) / iters
+        print("# %s: %.2f MB of DRAM traffic per call over %.1f launches" % (key, tot / 1e6, n))
+        traffic = json.load(open(traffic_out)) if traffic_out and os.path.exists(traffic_out) else {}
+        traffic[key] = dict(dram_bytes_per_launch=tot, launches=n,
+                            source="ncu dram__bytes_read.sum + dram__bytes_write.sum over every kernel of one call, " + path)
     if traffic_out:
         json.dump(traffic, open(traffic_out, "w"), indent=1)
 
