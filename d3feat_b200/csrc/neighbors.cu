@@ -184,6 +184,23 @@ __device__ __forceinline__ float sq_dist_rn(float qx, float qy, float qz, float4
   return r;
 }
 
+// One block size K of a 64-element bitonic sort of unique 32-bit keys, elements 2*lane and 2*lane+1 in one lane:
+// the exchanges at distance j >= 2 pair lane with lane ^ (j/2), the one at distance 1 stays inside the lane.
+template <int K>
+__device__ __forceinline__ void bitonic_block2(unsigned& ka, unsigned& kb, int lane) {
+  const bool asc = K == 64 || (lane & (K >> 1)) == 0;      // direction of the block elements 2*lane, 2*lane+1 sit in
+#pragma unroll
+  for (int j = K >> 1; j >= 2; j >>= 1) {
+    const unsigned oa = __shfl_xor_sync(0xffffffffu, ka, j >> 1), ob = __shfl_xor_sync(0xffffffffu, kb, j >> 1);
+    const bool keep_min = ((lane & (j >> 1)) == 0) == asc;
+    ka = keep_min ? min(ka, oa) : max(ka, oa);
+    kb = keep_min ? min(kb, ob) : max(kb, ob);
+  }
+  const unsigned lo = min(ka, kb), hi = max(ka, kb);
+  ka = asc ? lo : hi;
+  kb = asc ? hi : lo;
+}
+
 // FILL = false: counts only. FILL = true: sorted rows.
 template <bool FILL>
 __global__ void __launch_bounds__(kNbWarps * 32)
@@ -194,27 +211,36 @@ radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restri
                     int* __restrict__ out_idx) {
   const int Nq = dyn_rows(Nq_cap, nq_dev);
   const int pad_value = pad_dev ? __ldg(pad_dev) : pad_value_in;   // the shadow index = number of supports (device)
-  __shared__ int run_start[kNbWarps][9];
-  __shared__ int run_prefix[kNbWarps][10];
+  // per query: the 9 runs as (end of the run in the concatenated candidate numbering, sorted_pts offset of the run
+  // minus its start in that numbering): candidate t of run r is sorted_pts[t + adj[r]]
+  __shared__ int2 run_tab[kNbWarps][10];
   __shared__ Hit list[FILL ? kNbWarps : 1][FILL ? kNbListCap : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qi = blockIdx.x * kNbWarps + warp;
   if (qi >= Nq) return;  // warp-uniform
   const float qx = q[3 * (size_t)qi], qy = q[3 * (size_t)qi + 1], qz = q[3 * (size_t)qi + 2];
-  const int b = batch_of(q_start, B, qi);
+  int b;
+  if (B <= 32) {   // largest b with q_start[b] <= qi: one load per lane and a vote instead of a dependent search
+    const bool le = lane < B && __ldg(q_start + lane) <= qi;
+    b = max(__popc(__ballot_sync(0xffffffffu, le)) - 1, 0);
+  } else {
+    b = batch_of(q_start, B, qi);
+  }
   const int cx = cell_coord(qx, g.minx, g.inv_cell, g.nx);
   const int cy = cell_coord(qy, g.miny, g.inv_cell, g.ny);
   const int cz = cell_coord(qz, g.minz, g.inv_cell, g.nz);
 
-  // lanes 0..8: one (dy,dz) row each -> contiguous run over cells cx-1..cx+1
+  // lanes 0..8: one (dy,dz) row each -> contiguous run over cells cx-1..cx+1. The whole table holds at most
+  // kMaxGridCells = 2^27 cells (checked on the host), so 32-bit cell numbers are exact.
   int rs = 0, rl = 0;
   if (lane < 9) {
-    int yy = cy + (lane % 3) - 1, zz = cz + (lane / 3) - 1;
+    const int dz = (lane * 11) >> 5;            // lane / 3 for lane < 9
+    const int yy = cy + (lane - 3 * dz) - 1, zz = cz + dz - 1;
     if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
-      long long row = (long long)b * g.ncells + ((long long)zz * g.ny + yy) * g.nx;
-      int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+      const int row = b * (int)g.ncells + (zz * g.ny + yy) * g.nx;
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
       // cells x0..x1 of one (y, z) row are adjacent in the table: one contiguous run of sorted_pts
-      int s = cell_start[row + x0], e = cell_start[row + x1 + 1];
+      const int s = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);
       if (e > s) {
         rs = s;
         rl = e - s;
@@ -227,37 +253,31 @@ radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restri
     int t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  if (lane < 9) {
-    run_start[warp][lane] = rs;
-    run_prefix[warp][lane + 1] = inc;
-  }
-  if (lane == 0) run_prefix[warp][0] = 0;
+  if (lane < 9) run_tab[warp][lane] = make_int2(inc, rs - (inc - rl));
+  const int T = __shfl_sync(0xffffffffu, inc, 8);
+  if (lane == 9) run_tab[warp][9] = make_int2(0x7fffffff, 0);   // sentinel: the walk below never runs off the table
   __syncwarp();
-  const int T = run_prefix[warp][9];
 
   int n = 0;
-  // each lane walks the concatenated runs with stride 32, so its run index only moves forward
-  int r = 0, r_lo = 0, r_hi = run_prefix[warp][1], r_base = run_start[warp][0];
+  // each lane walks the concatenated runs with stride 32, so its run only moves forward (empty runs are skipped)
+  const int2* tp = &run_tab[warp][0];
+  int2 cur = *tp;
+  const unsigned below = (1u << lane) - 1u;
   for (int t0 = 0; t0 < T; t0 += 32) {
-    int t = t0 + lane;
+    const int t = t0 + lane;
     bool hit = false;
     float d2 = 0.f;
     int sidx = 0;
     if (t < T) {
-      while (t >= r_hi) {   // t < T = run_prefix[9] bounds r at 8; empty runs are skipped
-        ++r;
-        r_lo = r_hi;
-        r_hi = run_prefix[warp][r + 1];
-        r_base = run_start[warp][r];
-      }
-      float4 sp = sorted_pts[r_base + (t - r_lo)];
+      while (t >= cur.x) cur = *++tp;
+      const float4 sp = __ldg(sorted_pts + (t + cur.y));
       d2 = sq_dist_rn(qx, qy, qz, sp);
       sidx = (int)__float_as_uint(sp.w);
       hit = d2 < r2;
     }
-    unsigned m = __ballot_sync(0xffffffffu, hit);
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (FILL) {
-      int pos = n + __popc(m & ((1u << lane) - 1u));
+      const int pos = n + __popc(m & below);
       if (hit && pos < kNbListCap) {
         list[warp][pos].d2 = d2;
         list[warp][pos].idx = sidx;
@@ -277,7 +297,36 @@ radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restri
   if (out_max != nullptr && lane == 0) atomicMax(out_max, n);
   __syncwarp();
   int* row = out_idx + (size_t)qi * cols;
+  // Fast path for n <= 64 (every row of a calibrated pyramid): bitonic sort of 32-bit keys = the d2 bit pattern with
+  // its low 6 bits replaced by the hit's slot in `list`. Such keys are unique, one SHFL + one predicated min/max per
+  // compare-exchange (the exact 64-bit (d2, idx) keys below cost ~7 instructions), and the sorted slot gives the
+  // index back. The order is the exact (d2, idx) order iff no two hits agree in the upper 26 bits of d2 -- checked on
+  // the sorted keys (neighbours only); a row that fails (ties, or d2 values within 64 ulp: ~0.3 % of rows) falls
+  // through to the exact sort. Elements 2*lane and 2*lane+1 live in one lane, so the j = 1 exchanges need no shuffle.
+  bool sorted_fast = false;
   if (n <= 64) {
+    const int ia = 2 * lane, ib = ia + 1;
+    unsigned ka = 0xffffffffu, kb = 0xffffffffu;   // d2 < r2 is finite: real keys are below the padding
+    if (ia < n) ka = (__float_as_uint(list[warp][ia].d2) & ~63u) | (unsigned)ia;
+    if (ib < n) kb = (__float_as_uint(list[warp][ib].d2) & ~63u) | (unsigned)ib;
+    const int kmax = n <= 2 ? 2 : 2 << (31 - __clz(n - 1));   // next power of two >= n (warp-uniform)
+    if (kmax >= 2) bitonic_block2<2>(ka, kb, lane);            // kmax is warp-uniform
+    if (kmax >= 4) bitonic_block2<4>(ka, kb, lane);
+    if (kmax >= 8) bitonic_block2<8>(ka, kb, lane);
+    if (kmax >= 16) bitonic_block2<16>(ka, kb, lane);
+    if (kmax >= 32) bitonic_block2<32>(ka, kb, lane);
+    if (kmax >= 64) bitonic_block2<64>(ka, kb, lane);
+    // padding sorts last, so elements [0, n) are the hits; neighbours in one 64-ulp bucket -> exact path
+    const unsigned next_a = __shfl_down_sync(0xffffffffu, ka, 1);
+    const bool clash = (ib < n && ((ka ^ kb) < 64u)) || (ib + 1 < n && lane < 31 && ((kb ^ next_a) < 64u));
+    if (!__any_sync(0xffffffffu, clash)) {
+      if (ia < n && ia < cols) row[ia] = list[warp][ka & 63u].idx;
+      if (ib < n && ib < cols) row[ib] = list[warp][kb & 63u].idx;
+      sorted_fast = true;
+    }
+  }
+  if (sorted_fast) {
+  } else if (n <= 64) {
     // the common case: bitonic sort of <= 64 packed (d2, idx) keys in registers, two per lane (elements lane and
     // lane + 32). d2 >= +0, so the float's bit pattern orders like its value and the 64-bit key orders like
     // (d2, idx) -- the same total order as hit_less.
@@ -339,8 +388,8 @@ radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restri
       for (int t = lane; t < T; t += 32) {
         int r = 0;
 #pragma unroll
-        for (int k = 1; k < 9; ++k) r += (t >= run_prefix[warp][k]) ? 1 : 0;
-        float4 sp = sorted_pts[run_start[warp][r] + (t - run_prefix[warp][r])];
+        for (int k = 0; k < 8; ++k) r += (t >= run_tab[warp][k].x) ? 1 : 0;
+        float4 sp = sorted_pts[t + run_tab[warp][r].y];
         float d2 = sq_dist_rn(qx, qy, qz, sp);
         int si = (int)__float_as_uint(sp.w);
         if (d2 < r2 && hit_less(last_d, last_i, d2, si) && hit_less(d2, si, best_d, best_i)) {
