@@ -439,7 +439,8 @@ __device__ __forceinline__ void split3(float x, unsigned& hi, unsigned& lo) {
 //  integer add-and-mask of split3 is two)
 
 template <int NT>
-__global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_fast_kernel(Stage1Params p) {
+__global__ void __launch_bounds__(kS1Warps * 32, NT == 4 ? 8 : (NT == 8 ? 5 : 3))
+kpconv_stage1_fast_kernel(Stage1Params p) {
   const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
   constexpr int K = 15;
   static_assert(NT % 4 == 0, "one float4 per four n-tiles");
@@ -460,20 +461,25 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_fast_kernel(Stage
   const unsigned Cin = (unsigned)p.Cin;
   int cnt = 0;
 
-  constexpr int CCH = NT * 8;   // channels per pass
-  for (int c0 = 0; c0 < p.Cin; c0 += CCH) {
+  constexpr int CCH = NT * 8;   // channels per pass; wide layers on few queries spread the passes over gridDim.y
+  for (int c0 = blockIdx.y * CCH; c0 < p.Cin; c0 += gridDim.y * CCH) {
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
     const float* fcol = p.feat + c0 + NT * g;
     asm volatile("" : "+l"(fcol));   // opaque: keep the pointer in registers instead of re-deriving it every step
 
+    // the indices of step h0 + 8 are fetched while step h0 computes: one dependent load per step, not two
+    unsigned ida_n = Ns, idb_n = Ns;
+    if (t < p.H) ida_n = (unsigned)__ldg(row);
+    if (t + 4 < p.H) idb_n = (unsigned)__ldg(row + 4);
     for (int h0 = 0; h0 < p.H; h0 += 8) {
-      unsigned ida = Ns, idb = Ns;
-      if (h0 + t < p.H) ida = (unsigned)__ldg(row + h0);
-      if (h0 + t + 4 < p.H) idb = (unsigned)__ldg(row + h0 + 4);
-      ida = min(ida, Ns);       // -1 padding of the non-batch op (0xffffffff) behaves like the shadow
-      idb = min(idb, Ns);
+      const unsigned ida = min(ida_n, Ns);       // -1 padding of the non-batch op (0xffffffff) behaves like the shadow
+      const unsigned idb = min(idb_n, Ns);
+      ida_n = Ns;
+      idb_n = Ns;
+      if (h0 + 8 + t < p.H) ida_n = (unsigned)__ldg(row + h0 + 8);
+      if (h0 + 12 + t < p.H) idb_n = (unsigned)__ldg(row + h0 + 12);
       const float4 spa = __ldg(&p.s4[ida]), spb = __ldg(&p.s4[idb]);
       float fa[NT], fb[NT];
 #pragma unroll
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_fast_kernel(Stage
       }
     }
   }
-  if (p.inv_nn != nullptr) {
+  if (p.inv_nn != nullptr && blockIdx.y == 0) {
     // lanes 0-3 (g == 0) hold the counts of the neighbour slots t, t+4 (mod 8) of every step: together all of them
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
@@ -752,9 +758,13 @@ static int launch_stage1(int K, const Stage1Params& p, cudaStream_t stream) {
     const bool fast = p.influence == D3F_INFLUENCE_LINEAR && !p.closest;
     static const bool no_pared = [] { const char* v = getenv("D3F_S1_PARED"); return v != nullptr && v[0] == '0'; }();
     if (fast && !DEFORM && !no_pared && (long long)(p.Ns + 1) * p.Cin < (1ll << 31)) {
+      // Cin >= 256 (levels 3-4: a few thousand queries): one warp per (query, 128-channel pass) instead of a warp
+      // walking the passes one after the other, as long as the queries alone do not fill the machine
+      const int passes = p.Cin / 128;
+      const dim3 grid16(blocks, passes > 1 && blocks < 8 * kNumSMs ? passes : 1);
       if (p.Cin == 32) kpconv_stage1_fast_kernel<4><<<blocks, kS1Warps * 32, 0, stream>>>(p);
       else if (p.Cin == 64) kpconv_stage1_fast_kernel<8><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-      else kpconv_stage1_fast_kernel<16><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+      else kpconv_stage1_fast_kernel<16><<<grid16, kS1Warps * 32, 0, stream>>>(p);
       D3F_LAUNCH_CHECK("kpconv_stage1_fast_kernel");
       return D3F_OK;
     }
@@ -809,7 +819,10 @@ struct Cin1Params {
 // 8 lanes per query (4 queries per warp): a lane walks neighbours sl, sl+8, ... and keeps the 15 partial sums
 // wf[k] in registers; a 3-step shuffle reduction inside the 8-lane group finishes wf, then the group's lanes split the
 // output channels with W[15, Cout] staged once per CTA in shared memory.
-__global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
+// FAST = linear influence, sum aggregation (every D3Feat model): the 45 kernel-point coordinates live in registers
+// instead of 45 shared-memory loads per neighbour, no closest-point bookkeeping, the weight is two FMAs around the MUFU.
+template <bool FAST>
+__global__ void __launch_bounds__(256, 3) kpconv_cin1_kernel(Cin1Params p) {
   const int Ns_ = dyn_rows(p.Ns, p.ns_dev), Nq_ = dyn_rows(p.Nq, p.nq_dev);
   constexpr int K = 15;
   extern __shared__ float c1_smem[];   // W[K*Cout] then Kp[K*3]
@@ -831,6 +844,34 @@ __global__ void __launch_bounds__(256) kpconv_cin1_kernel(Cin1Params p) {
 #pragma unroll
   for (int k = 0; k < K; ++k) wf[k] = 0.f;
   int nn = 0;
+  if (FAST) {
+    float kp[K * 3];
+#pragma unroll
+    for (int i = 0; i < K * 3; ++i) kp[i] = kp_s[i];
+    const float inv_scale = p.inv_scale;
+    // two-deep software pipeline over the lane's neighbours: index of h + 16 and point of h + 8 are in flight while
+    // neighbour h is evaluated (-1 padding -> the shadow entry Ns, as for slots beyond H)
+    const unsigned Nsu = (unsigned)Ns_;
+    unsigned id1 = Nsu, id2 = Nsu;
+    if (sl < p.H) id1 = min((unsigned)__ldg(row + sl), Nsu);
+    if (sl + 8 < p.H) id2 = min((unsigned)__ldg(row + sl + 8), Nsu);
+    float4 sp_n = __ldg(&p.s4[id1]);
+    for (int h = sl; h < p.H; h += 8) {
+      const float4 sp = sp_n;               // (x, y, z, feature); entry Ns = shadow point with feature 0
+      sp_n = __ldg(&p.s4[id2]);
+      id2 = Nsu;
+      if (h + 16 < p.H) id2 = min((unsigned)__ldg(row + h + 16), Nsu);
+      const float f = sp.w, rx = sp.x - qx, ry = sp.y - qy, rz = sp.z - qz;
+      nn += f > 0.f ? 1 : 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float dx = rx - kp[3 * k], dy = ry - kp[3 * k + 1], dz = rz - kp[3 * k + 2];
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1e-10f)));
+        const float wk = fmaxf(fmaf(-sqrt_approx(d2), inv_scale, 1.f), 0.f);
+        wf[k] = fmaf(wk, f, wf[k]);           // f = 0 for shadow neighbours
+      }
+    }
+  } else
   for (int h = sl; h < p.H; h += 8) {
     int id = row[h];
     if (id < 0 || id > Ns_) id = Ns_;
@@ -1007,7 +1048,10 @@ int kpconv_forward_impl(bool deform, const float* q, const float* s, const int* 
     c1.nq_dev = nq_dev; c1.ns_dev = ns_dev;
     const size_t c1_smem = (size_t)(K * Cout + K * 3) * sizeof(float);
     D3F_REQUIRE(c1_smem <= 48 * 1024, D3F_ERR_CAPACITY, "kpconv (Cin = 1): Cout=%d too wide for the first-layer kernel", Cout);
-    kpconv_cin1_kernel<<<ceil_div(ceil_div(Nq, 4) * 32, 256), 256, c1_smem, stream>>>(c1);
+    if (influence == D3F_INFLUENCE_LINEAR && mode == D3F_MODE_SUM)
+      kpconv_cin1_kernel<true><<<ceil_div(ceil_div(Nq, 4) * 32, 256), 256, c1_smem, stream>>>(c1);
+    else
+      kpconv_cin1_kernel<false><<<ceil_div(ceil_div(Nq, 4) * 32, 256), 256, c1_smem, stream>>>(c1);
     D3F_LAUNCH_CHECK("kpconv_cin1_kernel");
     return D3F_OK;
   }

@@ -19,7 +19,12 @@ def bench(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 res = []
-for lvl, (Cin, name) in enumerate([(32, "layer_0/resnetb_1/conv2"), (64, "layer_1/resnetb_0/conv2"), (128, "layer_2/resnetb_0/conv2")]):
+q0, idx0 = inputs["points"][0], inputs["neighbors"][0]
+ones = torch.ones((q0.shape[0], 1), device=dev)
+Kp, W = enc.store.get("layer_0/simple_0/kernel_points"), enc.store.get("layer_0/simple_0/weights")
+res.append("1->64@%d: %.3f ms" % (q0.shape[0], bench(lambda: co.KPConv_ops(q0, q0, idx0, ones, Kp, W, 0.03, "linear", "sum"))))
+for lvl, (Cin, name) in enumerate([(32, "layer_0/resnetb_1/conv2"), (64, "layer_1/resnetb_0/conv2"), (128, "layer_2/resnetb_0/conv2"),
+                                   (256, "layer_3/resnetb_0/conv2"), (512, "layer_4/resnetb_0/conv2")]):
     q, idx = inputs["points"][lvl], inputs["neighbors"][lvl]
     feat = torch.randn((q.shape[0], Cin), device=dev)
     Kp, W = enc.store.get(name + "/kernel_points"), enc.store.get(name + "/weights")
