@@ -366,6 +366,284 @@ static int launch_tc_s(const float* A, const float* A2, int K1, const float* Bp,
   return D3F_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streaming variant for the long-K, huge-M GEMMs of levels 0/1: the KPConv contractions [Nq, 15 Cin] x [15 Cin, Cout]
+// on 60k-240k rows with Cout <= 64 ("operand pipeline"). OPT-IN (D3F_TC_STREAM=1): measured
+// (scripts/gemm_probe.py, profiles/r2_notes.md section 7) it gains 10 % on the 240k-row contraction (0.157 -> 0.142 ms)
+// and nothing on the 60k-row ones, while it owns all 512 TMEM columns and ~200 KB of shared memory of every SM.
+// ONE persistent CTA per SM walks its tiles and the product is issued TRANSPOSED:
+//     D[2 BN, 256] += Wimg[2 BN, 8] . Ximg[256, 8]^T        one tcgen05.mma per K = 8 step instead of three
+//   rows    0..BN-1 = W_hi of the tile's output channels, BN..2BN-1 = W_lo   (the two packed images are adjacent in smem)
+//   columns 0..127  = X_hi of the tile's 128 rows,        128..255 = X_lo    (the split images are adjacent in smem)
+//   out[q][c] = D[c][q] + D[c][128+q] + D[BN+c][q]          (3xTF32; the lo*lo quadrant is ignored)
+// so the same shared-memory images serve with the operand roles swapped.
+//   * 8 producer warps: cp.async of the raw fp32 X pieces three k-chunks ahead, in-place hi/lo split, W images by TMA;
+//     the ring never drains between tiles;
+//   * 1 MMA warp: 4 MMAs per k-chunk into one of two 256-column TMEM accumulators (double-buffered by tile parity);
+//   * 4 epilogue warps (one TMEM lane quadrant each): 32 queries at a time, TMEM -> registers -> two partial tiles in
+//     shared memory (W_hi rows, W_lo rows) -> summed, epilogue applied, coalesced rows; overlaps the next tile's k-loop.
+// Barriers: full[s] / empty[s] per ring stage (chunk counter runs across tiles), acc_full[b] / acc_empty[b] per TMEM set.
+// One accumulator per tile: the write-back truncation (see TcAcc) is ~1.1e-8 K, so the host keeps K <= 1024 here.
+// What the three measured variants say (same 0.74-0.86 us per k-chunk and SM in all of them: twelve M=128 MMAs or
+// four M=64/128 x N=256 MMAs per chunk, 3 or 6 chunks of loads in flight): neither the tensor pipe nor the bytes in
+// flight bound these GEMMs -- the 3xTF32 split does. Per 16 KB chunk the SM moves 16 KB (cp.async write) + 16 KB (LDS)
+// + 32 KB (STS hi, lo) + 40 KB (operand reads of the MMAs) through shared memory: 104 KB at 128 B/clk = 0.41 us.
+constexpr int kStProdWarps = 8;
+constexpr int kStProdThreads = kStProdWarps * 32;
+constexpr int kStThreads = (kStProdWarps + 4 + 1) * 32;   // + 4 epilogue warps + the MMA warp
+
+template <int BN>
+struct StSmem {
+  static constexpr int kStages = 4;
+  static constexpr int kABytes = kTcBM * 128;               // one image (hi or lo) of the 128-row X tile
+  static constexpr int kBBytes = BN * 128;                  // one image of the BN-row W tile
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kPStride = BN + 1;                   // padded row of a partial tile
+  static constexpr int kPBytes = 2 * 32 * kPStride * 4;     // [W_hi | W_lo part][32 queries][BN + 1]
+  static constexpr int kTotal = kStages * kStageBytes + kPBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kCols = 512;                         // two accumulators of 256 columns
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kStThreads, 1)
+tc_gemm_stream_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1, const float* __restrict__ Bp,
+                      float* __restrict__ C, int Mcap, int N, int K, int Kpad, int Npad, Epilogue ep) {
+  const int M = ep.m_dev ? min(Mcap, max(__ldg(ep.m_dev) - ep.m_off, 0)) : Mcap;
+  const int nk = Kpad / kTcBK;
+  const int ntn = Npad / BN;
+  const int tiles = ceil_div(M, kTcBM) * ntn;                // n-tiles of one row block are neighbours: X stays in L2
+  if ((int)blockIdx.x >= tiles) return;                      // CTA-uniform, before any barrier / TMEM allocation
+  const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  extern __shared__ uint8_t smem_raw[];
+  using S = StSmem<BN>;
+  constexpr int kStages = S::kStages;
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* part_smem = smem + kStages * S::kStageBytes;
+  uint64_t* bars = (uint64_t*)(part_smem + ((S::kPBytes + 15) / 16) * 16);
+  uint64_t* full = bars;                       // [kStages] split images + weight images of a chunk complete
+  uint64_t* empty = full + kStages;            // [kStages] the MMAs that read the stage retired
+  uint64_t* acc_full = empty + kStages;        // [2]
+  uint64_t* acc_empty = acc_full + 2;          // [2]
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&full[s]), kStProdThreads + 1);     // + the TMA issuer's arrive.expect_tx
+      mbar_init(smem_u32(&empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&acc_full[b]), 1);
+      mbar_init(smem_u32(&acc_empty[b]), 4);                 // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kStProdWarps + 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)S::kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kStProdWarps) {
+    // ===================== producers ======================================================================
+    const int chunk = tid & 7;      // 16-byte chunk inside the 128-byte row
+    const int rsub = tid >> 3;      // 0..31: row inside a 32-row slab
+    const int total = my_tiles * nk;
+    int i_tile = (int)blockIdx.x, i_kt = 0, i_g = 0;         // the next chunk to copy: (tile, k-chunk), running number
+    auto issue_chunk = [&]() {
+      const int s = i_g % kStages;
+      const uint32_t ph = (uint32_t)(i_g / kStages) & 1u;
+      mbar_wait(smem_u32(&empty[s]), ph ^ 1u);               // stage free (its MMAs retired)
+      uint8_t* st = smem + s * S::kStageBytes;
+      const int m0 = (i_tile / ntn) * kTcBM, n0 = (i_tile % ntn) * BN;
+      int k0 = i_kt * kTcBK + chunk * 4;
+      const float* src = A;
+      int ld = K;
+      if (A2 != nullptr) {
+        ld = K1;
+        if (k0 >= K1) {
+          src = A2;
+          ld = K - K1;
+          k0 -= K1;
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < kTcBM / 32; ++it) {
+        const int row = it * 32 + rsub;
+        const int gm = m0 + row;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        const bool ok = gm < M && k0 < ld;
+        cp_async16_zfill(smem_u32(st + off), src + (size_t)(ok ? gm : 0) * ld + (ok ? k0 : 0), ok);
+      }
+      if (tid == 0) {
+        const uint32_t fb = smem_u32(&full[s]);
+        const float* slab = Bp + (size_t)i_kt * 2 * Npad * 32 + (size_t)n0 * 32;
+        mbar_arrive_expect_tx(fb, 2u * S::kBBytes);
+        tma_bulk_g2s(smem_u32(st + 2 * S::kABytes), slab, S::kBBytes, fb);
+        tma_bulk_g2s(smem_u32(st + 2 * S::kABytes + S::kBBytes), slab + (size_t)Npad * 32, S::kBBytes, fb);
+      }
+      ++i_g;
+      if (++i_kt == nk) {
+        i_kt = 0;
+        i_tile += (int)gridDim.x;
+      }
+    };
+    for (int i = 0; i < kStages - 1; ++i) {
+      if (i < total) issue_chunk();
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int g = 0; g < total; ++g) {
+      const int s = g % kStages;
+      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");   // this thread's pieces of chunk g landed
+      const uint32_t st_s = smem_u32(smem + s * S::kStageBytes);
+      float4 x[kTcBM / 32];
+#pragma unroll
+      for (int it = 0; it < kTcBM / 32; ++it) {
+        const int row = it * 32 + rsub;
+        x[it] = lds128(st_s + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4));
+      }
+#pragma unroll
+      for (int it = 0; it < kTcBM / 32; ++it) {
+        const int row = it * 32 + rsub;
+        const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+        float4 hi, lo;
+        split_tf32(x[it].x, hi.x, lo.x);
+        split_tf32(x[it].y, hi.y, lo.y);
+        split_tf32(x[it].z, hi.z, lo.z);
+        split_tf32(x[it].w, hi.w, lo.w);
+        sts128(st_s + off, hi);
+        sts128(st_s + S::kABytes + off, lo);
+      }
+      fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&full[s]));
+      if (i_g < total) issue_chunk();
+      asm volatile("cp.async.commit_group;" ::: "memory");        // possibly empty: keeps the group count uniform
+    }
+  } else if (warp < kStProdWarps + 4) {
+    // ===================== epilogue warps: accumulator b of tile i while the k-loop of tile i+1 runs =========
+    // quadrant ew holds D rows [ew * RQ, (ew + 1) * RQ): ew = 0, 1 -> W_hi rows of channels (ew & 1) * RQ + lane,
+    // ew = 2, 3 -> the W_lo rows of the same channels (M = 64: 16 rows per quadrant in lanes 0..15; M = 128: 32)
+    constexpr int RQ = BN / 2;
+    constexpr int PS = S::kPStride;
+    const int ew = warp - kStProdWarps;                      // == warp % 4: the TMEM lane quadrant this warp may read
+    const int et = tid - kStProdThreads;                     // 0..127 inside the epilogue group
+    const int wpart = ew >> 1;
+    const int ch = (ew & 1) * RQ + lane;                     // channel of this lane's accumulator row (lane < RQ)
+    const uint32_t part = smem_u32(part_smem);
+    const bool has_bn = ep.bn_scale != nullptr, has_bias = ep.bias != nullptr, has_res = ep.residual != nullptr;
+    const bool has_leaky = ep.leaky_alpha >= 0.f;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int t = (int)blockIdx.x + i * (int)gridDim.x;
+      const int m0 = (t / ntn) * kTcBM, n0 = (t % ntn) * BN;
+      const int b = i & 1;
+      mbar_wait(smem_u32(&acc_full[b]), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(b * 256);
+#pragma unroll 1
+      for (int q0 = 0; q0 < kTcBM; q0 += 32) {
+        if (m0 + q0 >= M) break;                             // uniform over the epilogue group
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)q0, v);                   // . x X_hi
+        if (wpart == 0) {
+          float w[32];
+          tmem_ld32(tacc + (uint32_t)(128 + q0), w);         // W_hi x X_lo
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+        }
+        if (lane < RQ) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sts32(part + (uint32_t)((wpart * 32 + j) * PS + ch) * 4u, v[j]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // 32 queries x BN channels: a warp writes 8 rows, lanes run along the channels (coalesced row segments)
+#pragma unroll 1
+        for (int rr = 0; rr < 8; ++rr) {
+          const int r = (et >> 5) * 8 + rr;
+          const int gm = m0 + q0 + r;
+          if (gm >= M) break;                                // warp-uniform
+          const float rs = ep.rowscale != nullptr ? ep.rowscale[gm] : 1.f;
+          const size_t orow = ep.row_map ? (size_t)ep.row_map[gm] : (size_t)gm;
+#pragma unroll
+          for (int c = lane; c < BN; c += 32) {
+            const int gn = n0 + c;
+            if (gn < N) {
+              float y = lds32(part + (uint32_t)(r * PS + c) * 4u) + lds32(part + (uint32_t)((32 + r) * PS + c) * 4u);
+              y *= rs;
+              if (has_bn) y = fmaf(y, ep.bn_scale[gn], ep.bn_shift[gn]);
+              if (has_bias) y += ep.bias[gn];
+              if (has_res) y += ep.residual[orow * N + gn];
+              if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
+              C[orow * N + gn] = y;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");      // the partial tiles are free again
+      }
+      // every lane's tcgen05.ld has completed (wait::ld inside tmem_ld32): hand the accumulator back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[b]));
+    }
+  } else {
+    // ===================== MMA issuer (one elected lane) ====================================================
+    const uint32_t idesc = make_idesc_tf32(2 * BN, 256);
+    int g = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(smem_u32(&acc_empty[b]), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // accumulator b drained (tile i - 2)
+      tc_fence_after();
+      for (int kt = 0; kt < nk; ++kt, ++g) {
+        const int s = g % kStages;
+        mbar_wait(smem_u32(&full[s]), (uint32_t)(g / kStages) & 1u);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + s * S::kStageBytes);
+          const uint64_t x_img = make_smem_desc(sa);                        // 256 rows: X_hi | X_lo
+          const uint64_t w_img = make_smem_desc(sa + 2 * S::kABytes);       // 2 BN rows: W_hi | W_lo
+          const uint32_t d = tmem_base + (uint32_t)(b * 256);
+#pragma unroll
+          for (int j = 0; j < kTcBK / 8; ++j) {
+            const uint64_t adv = (uint64_t)((j * 32) >> 4);   // +32 B per K = 8 step inside the swizzle atom
+            umma_tf32(d, w_img + adv, x_img + adv, idesc, (kt != 0 || j != 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty[s]));                       // stage free once these MMAs retire
+          if (kt == nk - 1) umma_commit(smem_u32(&acc_full[b]));  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == kStProdWarps + 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::kCols)
+                 : "memory");
+  }
+}
+
+template <int BN>
+static int launch_tc_stream(const float* A, const float* A2, int K1, const float* Bp, float* C, int M, int N, int K,
+                            const Epilogue& ep, cudaStream_t stream) {
+  using S = StSmem<BN>;
+  static bool configured = false;   // idempotent attribute set; benign if two host threads race
+  if (!configured) {
+    D3F_CUDA(cudaFuncSetAttribute(tc_gemm_stream_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    configured = true;
+  }
+  const int Kpad = tc_padded_k(K), Npad = tc_padded_n(N);
+  const long long tiles = (long long)ceil_div(M, kTcBM) * (Npad / BN);
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  tc_gemm_stream_kernel<BN><<<grid, kStThreads, S::kTotal, stream>>>(A, A2, K1, Bp, C, M, N, K, Kpad, Npad, ep);
+  D3F_LAUNCH_CHECK("tc_gemm_stream_kernel");
+  return D3F_OK;
+}
+
 // D3F_TC_SKINNY=0 disables the single-stage variant (A/B measurements); D3F_TC_SKINNY_CHUNKS caps its k-chunks
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -448,6 +726,14 @@ int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, cons
   // image is the same (Npad is a multiple of 128, hence of 64).
   if (bn == 128 && K <= 256 && M >= 8192) bn = 64;
   const int splits = split_ws != nullptr ? tc_gemm_splits(M, N, K) : 1;
+  // the streaming variant: enough row tiles to keep one persistent CTA per SM busy for several tiles
+  const bool stream_ok = env_int("D3F_TC_STREAM", 0) != 0;          // read per call: tests switch it on and off
+  const int stream_min_nk = env_int("D3F_TC_STREAM_MIN_CHUNKS", 8);
+  if (stream_ok && bn <= 64 && splits <= 1 && (long long)ceil_div(M, kTcBM) * (tc_padded_n(N) / bn) >= 2ll * kNumSMs &&
+      K <= 1024 && tc_padded_k(K) / kTcBK >= stream_min_nk) {
+    if (bn == 64) return launch_tc_stream<64>(A, A2, K1, Bp, C, M, N, K, ep, stream);
+    return launch_tc_stream<32>(A, A2, K1, Bp, C, M, N, K, ep, stream);
+  }
   switch (bn) {
     case 128: return launch_tc<128>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);
     case 64: return launch_tc<64>(A, A2, K1, Bp, C, M, N, K, ep, stream, splits, split_ws);

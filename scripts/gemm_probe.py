@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from d3feat_b200 import convolution_ops as co
 dev = torch.device("cuda", 0)
-shapes = [(4177, 3840, 256), (1204, 7680, 512), (26112, 480, 32), (240000, 32, 128), (240000, 64, 128), (60336, 64, 256), (1204, 1024, 2048)]
+shapes = [(4177, 3840, 256), (1204, 7680, 512), (26112, 480, 32), (240000, 32, 128), (240000, 64, 128), (60336, 64, 256), (1204, 1024, 2048),
+          (240000, 480, 32), (240000, 64, 32), (240000, 128, 32), (60336, 960, 64), (60336, 128, 64), (60336, 480, 32)]
 only = os.environ.get("ONLY_SHAPE")
 for i, (M, K, N) in enumerate(shapes):
     if only is not None and int(only) != i:
