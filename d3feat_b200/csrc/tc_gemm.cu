@@ -203,11 +203,19 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
         const int row = it * 16 + rsub;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         float4 hi, lo;
-        split_tf32(x[it].x, hi.x, lo.x);
-        split_tf32(x[it].y, hi.y, lo.y);
-        split_tf32(x[it].z, hi.z, lo.z);
-        split_tf32(x[it].w, hi.w, lo.w);
-        sts128(st_s + off, hi);
+        if (ep.raw_hi) {
+          // the tensor core reads only the upper 19 bits of an fp32 operand: the raw image IS the (truncated) hi part
+          lo.x = trunc_lo_tf32(x[it].x);
+          lo.y = trunc_lo_tf32(x[it].y);
+          lo.z = trunc_lo_tf32(x[it].z);
+          lo.w = trunc_lo_tf32(x[it].w);
+        } else {
+          split_tf32(x[it].x, hi.x, lo.x);
+          split_tf32(x[it].y, hi.y, lo.y);
+          split_tf32(x[it].z, hi.z, lo.z);
+          split_tf32(x[it].w, hi.w, lo.w);
+          sts128(st_s + off, hi);
+        }
         sts128(st_s + S::kABytes + off, lo);
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -237,13 +245,19 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
     // output row of tile row (warp*32 + lane): identity, or the caller's row map (KPConv walks its queries in
     // the hash grid's cell order and scatters the rows back)
     const int my_orow = (gm < M) ? (ep.row_map ? ep.row_map[gm] : gm) : 0;
+    const bool full_tile = rows_here == 32 && ep.row_map == nullptr && (!has_leaky || (ep.leaky_alpha >= 0.f && ep.leaky_alpha <= 1.f));
+    const float alpha_eff = has_leaky ? ep.leaky_alpha : 1.f;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       const int gn = n0 + c0 + lane;
       const bool col_ok = gn < N;
       // residual rows of this column chunk: all 32 coalesced loads are in flight before anything waits on them
       float res[32];
-      if (has_res) {
+      if (has_res && full_tile && n0 + c0 + 32 <= N) {
+        const float* rp = ep.residual + (size_t)(m0 + warp * 32) * N + gn;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) res[rr] = rp[(size_t)rr * N];
+      } else if (has_res) {
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) {
           const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
@@ -265,14 +279,29 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
       const float sc = (has_bn && col_ok) ? ep.bn_scale[gn] : 1.f;
       const float sh = (has_bn && col_ok) ? ep.bn_shift[gn] : 0.f;
       const float bi = (has_bias && col_ok) ? ep.bias[gn] : 0.f;
+      if (full_tile && n0 + c0 + 32 <= N) {
+        // interior tile (all but the last row block / column chunk), rows in place: no per-element predicates, no
+        // shuffles, one pointer bump per row. LeakyReLU with 0 <= alpha <= 1 is max(y, alpha y); alpha = 1: identity.
+        // (ncu of the level-0 unaries: 10.7k warp instructions per 128 x 64 tile, two thirds of them in this loop's
+        // address / predicate scaffolding; the kernel sat at 61 % issue-slot utilisation.)
+        float* cp = C + (size_t)(m0 + warp * 32) * N + gn;
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) {
-        const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
-        if (col_ok && rr < rows_here) {
+        for (int rr = 0; rr < 32; ++rr) {
           float y = fmaf(lds32(tile + (uint32_t)(rr * 33 + lane) * 4u), sc, sh) + bi;
           if (has_res) y += res[rr];
-          if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
-          C[(size_t)orow * N + gn] = y;
+          y = fmaxf(y, y * alpha_eff);
+          cp[(size_t)rr * N] = y;
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const int orow = __shfl_sync(0xffffffffu, my_orow, rr);
+          if (col_ok && rr < rows_here) {
+            float y = fmaf(lds32(tile + (uint32_t)(rr * 33 + lane) * 4u), sc, sh) + bi;
+            if (has_res) y += res[rr];
+            if (has_leaky) y = y > 0.f ? y : y * ep.leaky_alpha;
+            C[(size_t)orow * N + gn] = y;
+          }
         }
       }
       __syncwarp();
@@ -355,7 +384,7 @@ static int launch_tc_s(const float* A, const float* A2, int K1, const float* Bp,
   splits = ceil_div(nk, cps);
   Epilogue raw;
   raw.rowscale = nullptr; raw.bn_scale = nullptr; raw.bn_shift = nullptr; raw.bias = nullptr; raw.residual = nullptr;
-  raw.leaky_alpha = -1.f; raw.row_map = nullptr; raw.m_dev = ep.m_dev; raw.m_off = ep.m_off;
+  raw.leaky_alpha = -1.f; raw.row_map = nullptr; raw.m_dev = ep.m_dev; raw.m_off = ep.m_off; raw.raw_hi = ep.raw_hi;
   dim3 grid(Npad / BN, ceil_div(M, kTcBM), splits);
   tc_gemm_kernel<BN, STAGES, ACC><<<grid, kTcThreads, S::kTotal, stream>>>(A, A2, K1, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
   D3F_LAUNCH_CHECK("tc_gemm_kernel");
@@ -512,11 +541,19 @@ tc_gemm_stream_kernel(const float* __restrict__ A, const float* __restrict__ A2,
         const int row = it * 32 + rsub;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         float4 hi, lo;
-        split_tf32(x[it].x, hi.x, lo.x);
-        split_tf32(x[it].y, hi.y, lo.y);
-        split_tf32(x[it].z, hi.z, lo.z);
-        split_tf32(x[it].w, hi.w, lo.w);
-        sts128(st_s + off, hi);
+        if (ep.raw_hi) {
+          // the tensor core reads only the upper 19 bits of an fp32 operand: the raw image IS the (truncated) hi part
+          lo.x = trunc_lo_tf32(x[it].x);
+          lo.y = trunc_lo_tf32(x[it].y);
+          lo.z = trunc_lo_tf32(x[it].z);
+          lo.w = trunc_lo_tf32(x[it].w);
+        } else {
+          split_tf32(x[it].x, hi.x, lo.x);
+          split_tf32(x[it].y, hi.y, lo.y);
+          split_tf32(x[it].z, hi.z, lo.z);
+          split_tf32(x[it].w, hi.w, lo.w);
+          sts128(st_s + off, hi);
+        }
         sts128(st_s + S::kABytes + off, lo);
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -713,7 +750,7 @@ size_t tc_gemm_split_ws_floats(int M, int N, int K) {
   return (size_t)(8 * tiles * kTcBM * bn);
 }
 
-int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
+int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep_in, cudaStream_t stream,
             float* split_ws, const float* A2, int K1) {
   if (M <= 0 || N <= 0) return D3F_OK;
   D3F_REQUIRE(tc_gemm_supported(A, K), D3F_ERR_INVALID, "tc_gemm: needs K %% 4 == 0 and 16-byte aligned A");
@@ -726,6 +763,8 @@ int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, cons
   // image is the same (Npad is a multiple of 128, hence of 64).
   if (bn == 128 && K <= 256 && M >= 8192) bn = 64;
   const int splits = split_ws != nullptr ? tc_gemm_splits(M, N, K) : 1;
+  Epilogue ep = ep_in;
+  ep.raw_hi = env_int("D3F_TC_RAWHI", 0) != 0;
   // the streaming variant: enough row tiles to keep one persistent CTA per SM busy for several tiles
   const bool stream_ok = env_int("D3F_TC_STREAM", 0) != 0;          // read per call: tests switch it on and off
   const int stream_min_nk = env_int("D3F_TC_STREAM_MIN_CHUNKS", 8);
