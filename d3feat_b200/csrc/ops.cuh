@@ -15,7 +15,6 @@ struct Epilogue {
   const int* row_map;     // [M] or null: GEMM row m is written to output row row_map[m]
   const int* m_dev = nullptr;   // optional: actual row count in device memory (M is then the launch capacity)
   int m_off = 0;                // rows of *m_dev that precede this GEMM's row 0 (KPConv query chunks)
-  int raw_hi = 0;               // tcgen05 path: 1 = the raw fp32 image serves as the hi operand (set by tc_gemm)
 };
 int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream);
 

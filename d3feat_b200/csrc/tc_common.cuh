@@ -102,11 +102,6 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
-// remainder of x after TRUNCATION to TF32 (what tcgen05 kind::tf32 does to an fp32 operand it reads): x = trunc + lo
-__device__ __forceinline__ float trunc_lo_tf32(float x) {
-  return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-}
-
 // TMA 1D bulk copy global -> shared, completing `bytes` on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

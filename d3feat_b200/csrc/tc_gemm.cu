@@ -203,19 +203,11 @@ tc_gemm_kernel(const float* __restrict__ A, const float* __restrict__ A2, int K1
         const int row = it * 16 + rsub;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         float4 hi, lo;
-        if (ep.raw_hi) {
-          // the tensor core reads only the upper 19 bits of an fp32 operand: the raw image IS the (truncated) hi part
-          lo.x = trunc_lo_tf32(x[it].x);
-          lo.y = trunc_lo_tf32(x[it].y);
-          lo.z = trunc_lo_tf32(x[it].z);
-          lo.w = trunc_lo_tf32(x[it].w);
-        } else {
-          split_tf32(x[it].x, hi.x, lo.x);
-          split_tf32(x[it].y, hi.y, lo.y);
-          split_tf32(x[it].z, hi.z, lo.z);
-          split_tf32(x[it].w, hi.w, lo.w);
-          sts128(st_s + off, hi);
-        }
+        split_tf32(x[it].x, hi.x, lo.x);
+        split_tf32(x[it].y, hi.y, lo.y);
+        split_tf32(x[it].z, hi.z, lo.z);
+        split_tf32(x[it].w, hi.w, lo.w);
+        sts128(st_s + off, hi);
         sts128(st_s + S::kABytes + off, lo);
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -384,7 +376,7 @@ static int launch_tc_s(const float* A, const float* A2, int K1, const float* Bp,
   splits = ceil_div(nk, cps);
   Epilogue raw;
   raw.rowscale = nullptr; raw.bn_scale = nullptr; raw.bn_shift = nullptr; raw.bias = nullptr; raw.residual = nullptr;
-  raw.leaky_alpha = -1.f; raw.row_map = nullptr; raw.m_dev = ep.m_dev; raw.m_off = ep.m_off; raw.raw_hi = ep.raw_hi;
+  raw.leaky_alpha = -1.f; raw.row_map = nullptr; raw.m_dev = ep.m_dev; raw.m_off = ep.m_off;
   dim3 grid(Npad / BN, ceil_div(M, kTcBM), splits);
   tc_gemm_kernel<BN, STAGES, ACC><<<grid, kTcThreads, S::kTotal, stream>>>(A, A2, K1, Bp, split_ws, M, N, K, Kpad, Npad, cps, raw);
   D3F_LAUNCH_CHECK("tc_gemm_kernel");
@@ -541,19 +533,11 @@ tc_gemm_stream_kernel(const float* __restrict__ A, const float* __restrict__ A2,
         const int row = it * 32 + rsub;
         const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
         float4 hi, lo;
-        if (ep.raw_hi) {
-          // the tensor core reads only the upper 19 bits of an fp32 operand: the raw image IS the (truncated) hi part
-          lo.x = trunc_lo_tf32(x[it].x);
-          lo.y = trunc_lo_tf32(x[it].y);
-          lo.z = trunc_lo_tf32(x[it].z);
-          lo.w = trunc_lo_tf32(x[it].w);
-        } else {
-          split_tf32(x[it].x, hi.x, lo.x);
-          split_tf32(x[it].y, hi.y, lo.y);
-          split_tf32(x[it].z, hi.z, lo.z);
-          split_tf32(x[it].w, hi.w, lo.w);
-          sts128(st_s + off, hi);
-        }
+        split_tf32(x[it].x, hi.x, lo.x);
+        split_tf32(x[it].y, hi.y, lo.y);
+        split_tf32(x[it].z, hi.z, lo.z);
+        split_tf32(x[it].w, hi.w, lo.w);
+        sts128(st_s + off, hi);
         sts128(st_s + S::kABytes + off, lo);
       }
       fence_proxy_async();   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -750,7 +734,7 @@ size_t tc_gemm_split_ws_floats(int M, int N, int K) {
   return (size_t)(8 * tiles * kTcBM * bn);
 }
 
-int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep_in, cudaStream_t stream,
+int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, const Epilogue& ep, cudaStream_t stream,
             float* split_ws, const float* A2, int K1) {
   if (M <= 0 || N <= 0) return D3F_OK;
   D3F_REQUIRE(tc_gemm_supported(A, K), D3F_ERR_INVALID, "tc_gemm: needs K %% 4 == 0 and 16-byte aligned A");
@@ -763,8 +747,6 @@ int tc_gemm(const float* A, const float* Bp, float* C, int M, int N, int K, cons
   // image is the same (Npad is a multiple of 128, hence of 64).
   if (bn == 128 && K <= 256 && M >= 8192) bn = 64;
   const int splits = split_ws != nullptr ? tc_gemm_splits(M, N, K) : 1;
-  Epilogue ep = ep_in;
-  ep.raw_hi = env_int("D3F_TC_RAWHI", 0) != 0;
   // the streaming variant: enough row tiles to keep one persistent CTA per SM busy for several tiles
   const bool stream_ok = env_int("D3F_TC_STREAM", 0) != 0;          // read per call: tests switch it on and off
   const int stream_min_nk = env_int("D3F_TC_STREAM_MIN_CHUNKS", 8);

@@ -53,6 +53,28 @@ for _ in range(4):
     pipe.step(bp, bl)
 pipe.step(None, None)
 pipe.drain()
+# ---- round 2: static (sync-free) pyramid + CUDA graph pipeline, device-side row counts, runtime-K KPConv, the fused
+# persistent KPConv kernel, the streaming GEMM, the pared stage-1 / first-layer kernels (run by the encoders above)
+from d3feat_b200.encoder import GraphPipeline
+tbp, tbl = torch.from_numpy(bp).to(dev), torch.from_numpy(bl).to(dev)
+gp = GraphPipeline.for_batch(ence, tbp, tbl)
+gp.prime(tbp, tbl)
+for _ in range(3):
+    gp.step(tbp, tbl)
+gp.step(None, None)
+gp.check()
+rows = torch.tensor([350], dtype=torch.int32, device=dev)
+co.unary_convolution(torch.randn(400, 64, device=dev), torch.randn(64, 32, device=dev), rows=rows)
+for K in (7, 23):
+    co.KPConv_ops(q, q, idx, torch.randn(400, 16, device=dev), torch.randn(K, 3, device=dev) * 0.1, torch.randn(K, 16, 24, device=dev), 0.12, "linear", "sum")
+os.environ["D3F_FUSED_KPCONV"] = "1"
+qf = torch.from_numpy(rng.uniform(0, 1, (4000, 3)).astype(np.float32)).to(dev)   # >= 3552 queries: the fused kernel's floor
+idf = torch.from_numpy(rng.integers(0, 4001, (4000, 21)).astype(np.int32)).to(dev)
+co.KPConv_ops(qf, qf, idf, torch.randn(4000, 32, device=dev), torch.randn(15, 3, device=dev) * 0.1, torch.randn(15, 32, 32, device=dev), 0.12, "linear", "sum")
+os.environ["D3F_FUSED_KPCONV"] = "0"
+os.environ["D3F_TC_STREAM"] = "1"
+co.unary_convolution(torch.randn(38001, 256, device=dev), torch.randn(256, 48, device=dev))
+os.environ["D3F_TC_STREAM"] = "0"
 co.USE_TENSOR_CORES = False
 co.unary_convolution(torch.randn(300, 36, device=dev), torch.randn(36, 50, device=dev))
 co.KPConv_ops(q, q, idx, torch.randn(400, 32, device=dev), torch.randn(15, 3, device=dev) * 0.1, torch.randn(15, 32, 32, device=dev), 0.12, "linear", "sum")
