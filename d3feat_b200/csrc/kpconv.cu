@@ -534,6 +534,162 @@ kpconv_stage1_fast_kernel(Stage1Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The pared kernel with the gathers STAGED through shared memory. ncu of the kernel above (profiles/r2_stage1_ncu.txt):
+// the L1 data pipe is the bound (l1tex__data_pipe_lsu_wavefronts 88 % of peak) -- a 128-bit warp load is served a
+// quarter-warp at a time, one wavefront per cache line the quarter touches, and in the mma fragment layout
+// (lane = 4 g + t, neighbour <-> t) every quarter holds four neighbours: 16 wavefronts per row load instead of 4, and
+// the same for the packed points. Here the rows of a step arrive by cp.async in the COALESCED assignment (the 8 lanes
+// of a quarter-warp copy the 128 contiguous bytes of one row: 4 wavefronts per instruction; the shadow row is a
+// zero-fill), and the fragment lanes read them back with conflict-free 128-bit shared loads (XOR-swizzled chunks);
+// lanes 0..7 fetch the step's 8 neighbour ids with one access and copy the 8 packed points. Per 8-neighbour step and
+// 32-channel pass: ~35 wavefronts instead of ~70. Double-buffered per warp; no CTA-level synchronisation.
+__device__ __forceinline__ uint32_t s1_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s1_cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ float4 s1_lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// swizzle of the 16-byte chunk index inside a 128-byte segment, by row & 3, such that the 8 (row, chunk) pairs a
+// quarter-warp reads in fragment layout fall into 8 different bank groups
+template <int NT>
+__device__ __forceinline__ int s1_swz(int r3) {
+  return NT == 4 ? 2 * r3 : (NT == 8 ? ((r3 & 1) | ((r3 & 2) << 1)) : r3);
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kS1Warps * 32, NT == 4 ? 8 : (NT == 8 ? 5 : 3))
+kpconv_stage1_staged_kernel(Stage1Params p) {
+  constexpr int K = 15;
+  constexpr int ROWB = NT * 32;            // bytes of one row of a channel pass (NT * 8 channels)
+  constexpr int BUFB = 8 * ROWB + 128;     // 8 rows + 8 packed points
+  __shared__ __align__(128) unsigned char stage_sm[kS1Warps][2][BUFB];
+  const int Ns_ = dyn_rows(p.Ns, p.ns_dev), n1_ = min(p.n1, dyn_rows(p.Nq, p.nq_dev));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n = p.n0 + blockIdx.x * kS1Warps + warp;
+  if (n >= n1_) return;  // warp-uniform
+  const int kA = g, kB = g + 8;
+  const bool validB = kB < K;
+  const float kax = p.Kp[3 * kA], kay = p.Kp[3 * kA + 1], kaz = p.Kp[3 * kA + 2];
+  const float kbx = validB ? p.Kp[3 * kB] : 1e6f, kby = validB ? p.Kp[3 * kB + 1] : 1e6f,
+              kbz = validB ? p.Kp[3 * kB + 2] : 1e6f;
+  const int qid = p.order ? p.order[n] : n;
+  const float qx = p.q[3 * (size_t)qid], qy = p.q[3 * (size_t)qid + 1], qz = p.q[3 * (size_t)qid + 2];
+  const int* rowq = p.idx + (size_t)qid * p.H;
+  const float inv_scale = p.inv_scale;
+  const unsigned Ns = (unsigned)Ns_;
+  const unsigned Cin = (unsigned)p.Cin;
+  const uint32_t base = s1_smem_u32(&stage_sm[warp][0][0]);
+  const int cr = lane >> 3, cc = lane & 7;             // copy role: rows cr and cr + 4, chunk cc of every 128-byte segment
+  // per-lane shared-memory offsets, computed once and pinned (ptxas otherwise re-derives them from %tid every step)
+  uint32_t wr_row = (uint32_t)(cr * ROWB + (cc ^ s1_swz<NT>(cr & 3)) * 16);   // rows cr and cr + 4 share row & 3
+  uint32_t wr_s4 = (uint32_t)(8 * ROWB + lane * 16);
+  uint32_t rd_s4 = (uint32_t)(8 * ROWB + t * 16);
+  uint32_t rd_row[NT / 4];                             // fragment role: rows t and t + 4, channels NT g + v ..
+#pragma unroll
+  for (int v = 0; v < NT; v += 4) {
+    const int chunk = g * (NT / 4) + v / 4;
+    rd_row[v / 4] = (uint32_t)(t * ROWB + (chunk & ~7) * 16 + (((chunk & 7) ^ s1_swz<NT>(t)) * 16));
+    asm volatile("" : "+r"(rd_row[v / 4]));
+  }
+  asm volatile("" : "+r"(wr_row), "+r"(wr_s4), "+r"(rd_s4));
+  int cnt = 0;
+
+  constexpr int CCH = NT * 8;
+  for (int c0 = blockIdx.y * CCH; c0 < p.Cin; c0 += gridDim.y * CCH) {
+    float acc[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    const float* fsrc = p.feat + c0 + 4 * cc;
+    asm volatile("" : "+l"(fsrc));
+    auto load_ids = [&](int h0) -> unsigned {
+      unsigned v = Ns;                                   // slots beyond H and the -1 padding: the shadow
+      if (lane < 8 && h0 + lane < p.H) v = (unsigned)__ldg(rowq + h0 + lane);
+      return min(v, Ns);
+    };
+    auto issue = [&](unsigned idv, uint32_t buf) {
+      if (lane < 8) s1_cp_async16(buf + wr_s4, p.s4 + idv, true);
+      const unsigned i0 = __shfl_sync(0xffffffffu, idv, cr), i1 = __shfl_sync(0xffffffffu, idv, cr + 4);
+      const bool ok0 = i0 < Ns, ok1 = i1 < Ns;
+      const float* s0 = fsrc + (size_t)((ok0 ? i0 : 0u) * Cin);
+      const float* s1 = fsrc + (size_t)((ok1 ? i1 : 0u) * Cin);
+#pragma unroll
+      for (int seg = 0; seg < ROWB / 128; ++seg) {
+        s1_cp_async16(buf + wr_row + seg * 128, s0 + seg * 32, ok0);
+        s1_cp_async16(buf + wr_row + 4 * ROWB + seg * 128, s1 + seg * 32, ok1);
+      }
+    };
+    uint32_t cur = base, nxt = base + BUFB;
+    unsigned idv_n = load_ids(0);
+    issue(idv_n, cur);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    idv_n = load_ids(8);
+    for (int h0 = 0; h0 < p.H; h0 += 8) {
+      if (h0 + 8 < p.H) issue(idv_n, nxt);               // the rows of step h0 + 8 fly while step h0 computes
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      idv_n = load_ids(h0 + 16);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const float4 spa = s1_lds128(cur + rd_s4), spb = s1_lds128(cur + rd_s4 + 64);
+      float fa[NT], fb[NT];
+#pragma unroll
+      for (int v = 0; v < NT; v += 4) {
+        const float4 x = s1_lds128(cur + rd_row[v / 4]), y = s1_lds128(cur + rd_row[v / 4] + 4 * ROWB);
+        fa[v] = x.x; fa[v + 1] = x.y; fa[v + 2] = x.z; fa[v + 3] = x.w;
+        fb[v] = y.x; fb[v + 1] = y.y; fb[v + 2] = y.z; fb[v + 3] = y.w;
+      }
+      if (c0 == 0) cnt += (spa.w > 0.f ? 1 : 0) + (spb.w > 0.f ? 1 : 0);
+      const float rax = spa.x - qx, ray = spa.y - qy, raz = spa.z - qz;
+      const float rbx = spb.x - qx, rby = spb.y - qy, rbz = spb.z - qz;
+      auto weight = [&](float rx, float ry, float rz, float kx, float ky, float kz) {
+        const float dx = rx - kx, dy = ry - ky, dz = rz - kz;
+        const float d2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, 1e-10f)));     // d^2 + 1e-10 (:215)
+        return fmaxf(fmaf(-sqrt_approx(d2), inv_scale, 1.f), 0.f);             // 1 - d / (2 extent), clipped
+      };
+      unsigned ah[4], al[4];
+      split3(weight(rax, ray, raz, kax, kay, kaz), ah[0], al[0]);
+      split3(weight(rax, ray, raz, kbx, kby, kbz), ah[1], al[1]);
+      split3(weight(rbx, rby, rbz, kax, kay, kaz), ah[2], al[2]);
+      split3(weight(rbx, rby, rbz, kbx, kby, kbz), ah[3], al[3]);
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        unsigned bh0, bl0, bh1, bl1;
+        split3(fa[i], bh0, bl0);
+        split3(fb[i], bh1, bl1);
+        mma_tf32(acc[i], ah, bh0, bh1);
+        mma_tf32(acc[i], al, bh0, bh1);
+        mma_tf32(acc[i], ah, bl0, bl1);
+      }
+      __syncwarp();   // every lane is done with the buffer before the next iteration's copies overwrite it
+      const uint32_t tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+
+    float* dst = p.wf + (size_t)(n - p.n0) * K * p.Cin + c0 + 2 * NT * t;
+#pragma unroll
+    for (int v = 0; v < NT; v += 4) {
+      *reinterpret_cast<float4*>(dst + (size_t)kA * p.Cin + v) = make_float4(acc[v][0], acc[v + 1][0], acc[v + 2][0], acc[v + 3][0]);
+      *reinterpret_cast<float4*>(dst + (size_t)kA * p.Cin + NT + v) = make_float4(acc[v][1], acc[v + 1][1], acc[v + 2][1], acc[v + 3][1]);
+      if (validB) {
+        *reinterpret_cast<float4*>(dst + (size_t)kB * p.Cin + v) = make_float4(acc[v][2], acc[v + 1][2], acc[v + 2][2], acc[v + 3][2]);
+        *reinterpret_cast<float4*>(dst + (size_t)kB * p.Cin + NT + v) = make_float4(acc[v][3], acc[v + 1][3], acc[v + 2][3], acc[v + 3][3]);
+      }
+    }
+  }
+  if (p.inv_nn != nullptr && blockIdx.y == 0) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    if (lane == 0) p.inv_nn[n - p.n0] = 1.f / (float)max(cnt, 1);
+  }
+}
+
 // FAST = the D3Feat configuration (KP_influence = linear, aggregation = sum) resolved at compile time; the
 // generic instantiation keeps the runtime switches for constant / gaussian / closest.
 template <int NT, bool DEFORM, bool FAST>
@@ -762,6 +918,15 @@ static int launch_stage1(int K, const Stage1Params& p, cudaStream_t stream) {
       // walking the passes one after the other, as long as the queries alone do not fill the machine
       const int passes = p.Cin / 128;
       const dim3 grid16(blocks, passes > 1 && blocks < 8 * kNumSMs ? passes : 1);
+      const char* sv = getenv("D3F_S1_STAGED");          // read per call: tests switch it
+      const int staged = sv ? atoi(sv) : 0;
+      if (staged) {
+        if (p.Cin == 32) kpconv_stage1_staged_kernel<4><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+        else if (p.Cin == 64) kpconv_stage1_staged_kernel<8><<<blocks, kS1Warps * 32, 0, stream>>>(p);
+        else kpconv_stage1_staged_kernel<16><<<grid16, kS1Warps * 32, 0, stream>>>(p);
+        D3F_LAUNCH_CHECK("kpconv_stage1_staged_kernel");
+        return D3F_OK;
+      }
       if (p.Cin == 32) kpconv_stage1_fast_kernel<4><<<blocks, kS1Warps * 32, 0, stream>>>(p);
       else if (p.Cin == 64) kpconv_stage1_fast_kernel<8><<<blocks, kS1Warps * 32, 0, stream>>>(p);
       else kpconv_stage1_fast_kernel<16><<<grid16, kS1Warps * 32, 0, stream>>>(p);

@@ -284,3 +284,25 @@ def test_kpconv_fused_kernel_matches_restatement_and_two_kernel_path(cuda, monke
     # bit-reproducible (no atomics, fixed tile schedule)
     monkeypatch.setenv("D3F_FUSED_KPCONV", "1")
     assert torch.equal(co.KPConv_ops(*args, 0.05, "linear", "sum", epilogue=epi), fused)
+
+
+@pytest.mark.parametrize("Cin,Cout,Nq,Ns,H", [(32, 32, 3000, 3000, 40), (64, 64, 900, 3000, 37), (128, 128, 700, 700, 40),
+                                              (512, 512, 300, 300, 21)])
+def test_kpconv_staged_stage1_variant(cuda, monkeypatch, Cin, Cout, Nq, Ns, H):
+    """D3F_S1_STAGED=1: stage 1 with the gathered rows staged through shared memory (cp.async in the coalesced
+    assignment, zero-filled shadow rows, swizzled conflict-free fragment reads, double-buffered per warp) -- same
+    result as the default register-gather kernel (both 3xTF32; identical arithmetic per element) and within 1e-4 of
+    the float64 restatement. H not a multiple of 8, strided queries, several channel passes (Cin = 512)."""
+    from d3feat_b200 import convolution_ops as co
+    rng = np.random.default_rng(Cin + H)
+    extent = 0.06 if Ns >= 2000 else 0.12
+    q, s, idx, f, Kp, W = make_case(rng, Nq, Ns, H, Cin, Cout, extent=extent)
+    f[::7] = -np.abs(f[::7])
+    args = [t(x, cuda) for x in (q, s, idx, f, Kp, W)]
+    monkeypatch.setenv("D3F_S1_STAGED", "0")
+    base = co.KPConv_ops(*args, extent, "linear", "sum")
+    monkeypatch.setenv("D3F_S1_STAGED", "1")
+    staged = co.KPConv_ops(*args, extent, "linear", "sum")
+    ref = ok.kpconv_ops(q, s, idx, f, Kp, W, extent, "linear", "sum", dtype=np.float64)
+    assert rel_err(staged.cpu().numpy(), ref) < RTOL
+    assert torch.equal(staged, base)
