@@ -729,22 +729,26 @@ __global__ void __launch_bounds__(kS1Warps * 32) kpconv_stage1_mma_kernel(Stage1
     float acc[NT][4];
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-    const float* fcol = p.feat + c0 + NT * g;
+    // row base as an opaque byte pointer and row offsets as one unsigned 32 x 32 -> 64 multiply-add: ptxas otherwise
+    // re-derives the pointer from %tid and rebuilds the 64-bit address with five instructions per row load
+    const char* fcol = reinterpret_cast<const char*>(p.feat + c0 + NT * g);
+    asm volatile("" : "+l"(fcol));
+    const unsigned cin_bytes = (unsigned)p.Cin * 4u;
 
     for (int h0 = 0; h0 < p.H; h0 += 8) {
       const int ha = h0 + t, hb = h0 + t + 4;
-      int ida = ha < p.H ? row[ha] : Ns_, idb = hb < p.H ? row[hb] : Ns_;
-      if (ida < 0 || ida > Ns_) ida = Ns_;
-      if (idb < 0 || idb > Ns_) idb = Ns_;
+      unsigned ida = ha < p.H ? (unsigned)row[ha] : (unsigned)Ns_, idb = hb < p.H ? (unsigned)row[hb] : (unsigned)Ns_;
+      ida = min(ida, (unsigned)Ns_);        // -1 padding (0xffffffff) and out-of-range ids: the shadow entry
+      idb = min(idb, (unsigned)Ns_);
       const float4 spa = __ldg(&p.s4[ida]), spb = __ldg(&p.s4[idb]);
-      const bool reala = ida < Ns_, realb = idb < Ns_;
+      const bool reala = ida < (unsigned)Ns_, realb = idb < (unsigned)Ns_;
       // feature rows in fragment layout (issued before the weight math: latency overlaps it). A register-
       // pipelined variant (rows one step ahead) was measured SLOWER: occupancy (63 vs 93 regs) matters more.
       float fa[NT], fb[NT];
 #pragma unroll
       for (int v = 0; v < NT; v += 4) {
-        float4 x = reala ? __ldg(reinterpret_cast<const float4*>(fcol + (size_t)ida * p.Cin + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 y = realb ? __ldg(reinterpret_cast<const float4*>(fcol + (size_t)idb * p.Cin + v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = reala ? __ldg(reinterpret_cast<const float4*>(fcol + (size_t)ida * cin_bytes + 4 * v)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 y = realb ? __ldg(reinterpret_cast<const float4*>(fcol + (size_t)idb * cin_bytes + 4 * v)) : make_float4(0.f, 0.f, 0.f, 0.f);
         fa[v] = x.x; fa[v + 1] = x.y; fa[v + 2] = x.z; fa[v + 3] = x.w;
         fb[v] = y.x; fb[v + 1] = y.y; fb[v + 2] = y.z; fb[v + 3] = y.w;
       }
