@@ -131,3 +131,34 @@ def test_pyramid_buffers_and_spec_on_cpu():
     assert [round(float(specd.conv_radius[l]), 3) for l in range(5)] == [0.75, 1.5, 3.0, 6.0, 12.0]
     assert [round(float(specd.pool_radius[l]), 3) for l in range(4)] == [0.75, 1.5, 3.0, 12.0]
     assert round(float(specd.up_radius[3]), 3) == 24.0
+
+
+def test_shape_buckets_and_per_level_capacities_on_cpu():
+    """Host side of the sync-free form (encoder.GraphPipeline): capacities of a shape bucket and the per-level buffer
+    shapes of a slot. A level's pool matrix has the rows of the NEXT level and the columns of this level's cap; the
+    upsample matrix the rows of this level (datasets/common.py:1358-1372)."""
+    import torch
+    from d3feat_b200 import pyramid as pyr, synth
+    sizes = [240000, 60336, 15430, 4177, 1204]
+    caps = pyr.bucket_capacities(sizes)
+    assert caps == [270080, 68096, 17664, 4864, 1536]
+    assert all(c % 256 == 0 and c >= 1.125 * n for c, n in zip(caps, sizes))
+    assert pyr.bucket_capacities([0, 1]) == [256, 256]                 # empty levels still get a launchable buffer
+    assert pyr.bucket_capacities(sizes, slack=1.0, quantum=128) == [240128, 60416, 15616, 4352, 1280]
+    cfg = synth.Config(architecture=synth.ARCH_ENCODER)
+    limits = [40, 39, 38, 37, 36]
+    small = [1000, 300, 90, 30, 10]
+    buf = pyr.PyramidBuffers(cfg, limits, capacity=small, n_clouds=3, device=torch.device("cpu"),
+                             bbox=np.array([0, 0, 0, 1, 1, 1], np.float32))
+    assert buf.caps == small and buf.capacity == 1000
+    assert [tuple(b.shape) for b in buf.nb] == [(1000, 40), (300, 39), (90, 38), (30, 37), (10, 36)]
+    assert [tuple(buf.pool[l].shape) for l in range(4)] == [(300, 40), (90, 39), (30, 38), (10, 37)]
+    assert [tuple(buf.up[l].shape) for l in range(4)] == [(1000, 40), (300, 39), (90, 38), (30, 37)]
+    assert [tuple(buf.pts[l].shape) for l in range(1, 5)] == [(300, 3), (90, 3), (30, 3), (10, 3)]
+    assert tuple(buf.points0.shape) == (1000, 3) and tuple(buf.lengths0.shape) == (3,)
+    assert buf.features0.shape == (1000, cfg.in_features_dim) and float(buf.features0.min()) == 1.0
+    assert buf.counts.dtype == torch.int32 and int(buf.counts.abs().sum()) == 0 and int(buf.status[0]) == 0
+    assert buf.bbox.dtype == np.float32 and buf.bbox.shape == (6,)
+    assert buf.fits(1000, 3, limits) and not buf.fits(1000, 2, limits)
+    with pytest.raises(AssertionError):
+        pyr.PyramidBuffers(cfg, limits, capacity=[10, 5], n_clouds=1, device=torch.device("cpu"))
