@@ -5,6 +5,8 @@
 // 432-440, 1280-1289): every support of the same cloud with d2 < r2, d2 = ((dx*dx)+dy*dy)+dz*dz evaluated in
 // fp32 with separately rounded mul/add (__fmul_rn/__fadd_rn: nvcc would otherwise contract to FMA),
 // r2 = radius*radius in fp32, rows ascending in (d2, index), padded with pad_value.
+#include <stdlib.h>
+
 #include "ops.cuh"
 #include "sort.cuh"
 
@@ -414,6 +416,217 @@ radius_query_kernel(const float* __restrict__ q, int Nq_cap, const int* __restri
   for (int c = n + lane; c < cols; c += 32) row[c] = pad_value;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// The same query with TWO queries per warp (16 lanes each). ncu of the kernel above (profiles/r2_radius_query_ncu.txt):
+// instruction bound, ~600 warp instructions per query of which 165 are the prologue (nine lanes busy) and ~170 the
+// 64-key sort (two keys per lane, 15 of 21 exchange levels through shuffles). With 16 lanes per query the prologue
+// serves two queries per warp instruction and a lane holds FOUR keys (elements 4 l .. 4 l + 3): only the exchanges at
+// distance >= 4 need a shuffle (10 of 21 levels). The candidate loop is unchanged in lane efficiency (~110 candidates
+// in steps of 16; the warp runs to the longer of its two lists).
+// Rows whose sorted 32-bit keys clash (ties, d2 within 64 ulp) and rows with more than 64 hits take an exact rank sort
+// over the shared-memory list (up to kNbListCap2 hits), denser rows the re-scan path -- per half-warp, under a
+// half-warp mask, so the other query of the warp is not held up by warp-wide shuffles.
+constexpr int kNbListCap2 = 256;   // hits kept in shared memory per query (16 queries per CTA: 32 KB)
+
+__device__ __forceinline__ void cex_dir(unsigned& a, unsigned& b, bool asc) {   // in-lane compare-exchange
+  const unsigned lo = min(a, b), hi = max(a, b);
+  a = asc ? lo : hi;
+  b = asc ? hi : lo;
+}
+// block size K of the 64-element bitonic sort, four elements per lane (i = 4 hl + e), 16 lanes
+template <int K>
+__device__ __forceinline__ void bitonic_block4(unsigned (&k)[4], int hl) {
+  if (K == 2) {
+    cex_dir(k[0], k[1], true);
+    cex_dir(k[2], k[3], false);
+    return;
+  }
+  const bool asc = K == 64 || (hl & (K >> 2)) == 0;      // all four elements of a lane sit in the same block for K >= 4
+#pragma unroll
+  for (int j = K >> 1; j >= 4; j >>= 1) {
+    const bool keep_min = ((hl & (j >> 2)) == 0) == asc;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const unsigned o = __shfl_xor_sync(0xffffffffu, k[e], j >> 2);
+      k[e] = keep_min ? min(k[e], o) : max(k[e], o);
+    }
+  }
+  cex_dir(k[0], k[2], asc);
+  cex_dir(k[1], k[3], asc);
+  cex_dir(k[0], k[1], asc);
+  cex_dir(k[2], k[3], asc);
+}
+
+__global__ void __launch_bounds__(kNbWarps * 32)
+radius_query2_kernel(const float* __restrict__ q, int Nq_cap, const int* __restrict__ nq_dev,
+                     const int* __restrict__ q_start, int B, NbGrid g, const float4* __restrict__ sorted_pts,
+                     const int* __restrict__ cell_start, float r2, int cols, int pad_value_in,
+                     const int* __restrict__ pad_dev, int* __restrict__ counts, int* __restrict__ out_max,
+                     int* __restrict__ out_idx) {
+  const int Nq = dyn_rows(Nq_cap, nq_dev);
+  const int pad_value = pad_dev ? __ldg(pad_dev) : pad_value_in;
+  __shared__ int2 run_tab[kNbWarps * 2][10];
+  __shared__ Hit list[kNbWarps * 2][kNbListCap2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hw = lane >> 4, hl = lane & 15;
+  const int slot = warp * 2 + hw;
+  const int qi_raw = (blockIdx.x * kNbWarps + warp) * 2 + hw;
+  if ((blockIdx.x * kNbWarps + warp) * 2 >= Nq) return;   // warp-uniform: both queries beyond the end
+  const bool qvalid = qi_raw < Nq;
+  const int qi = qvalid ? qi_raw : Nq - 1;                 // an odd tail half idles on a copy of the last query
+  const unsigned hmask = 0xffffu << (16 * hw);
+  const float qx = q[3 * (size_t)qi], qy = q[3 * (size_t)qi + 1], qz = q[3 * (size_t)qi + 2];
+  int b;
+  if (B <= 16) {
+    const bool le = hl < B && __ldg(q_start + hl) <= qi;
+    b = max(__popc((__ballot_sync(0xffffffffu, le) >> (16 * hw)) & 0xffffu) - 1, 0);
+  } else {
+    b = batch_of(q_start, B, qi);
+  }
+  const int cx = cell_coord(qx, g.minx, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.miny, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.minz, g.inv_cell, g.nz);
+  int rs = 0, rl = 0;
+  if (hl < 9) {
+    const int dz = (hl * 11) >> 5;            // hl / 3 for hl < 9
+    const int yy = cy + (hl - 3 * dz) - 1, zz = cz + dz - 1;
+    if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+      const int row = b * (int)g.ncells + (zz * g.ny + yy) * g.nx;
+      const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+      const int s = __ldg(cell_start + row + x0), e = __ldg(cell_start + row + x1 + 1);
+      if (e > s) {
+        rs = s;
+        rl = e - s;
+      }
+    }
+  }
+  int inc = rl;
+#pragma unroll
+  for (int o = 1; o < 16; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o, 16);
+    if (hl >= o) inc += t;
+  }
+  if (hl < 9) run_tab[slot][hl] = make_int2(inc, rs - (inc - rl));
+  int T = __shfl_sync(0xffffffffu, inc, 8, 16);
+  if (!qvalid) T = 0;
+  if (hl == 9) run_tab[slot][9] = make_int2(0x7fffffff, 0);
+  __syncwarp();
+  const int Tmax = max(T, __shfl_xor_sync(0xffffffffu, T, 16));
+
+  int n = 0;
+  const int2* tp = &run_tab[slot][0];
+  int2 cur = *tp;
+  const unsigned below = (1u << hl) - 1u;
+  for (int t0 = 0; t0 < Tmax; t0 += 16) {
+    const int t = t0 + hl;
+    bool hit = false;
+    float d2 = 0.f;
+    int sidx = 0;
+    if (t < T) {
+      while (t >= cur.x) cur = *++tp;
+      const float4 sp = __ldg(sorted_pts + (t + cur.y));
+      d2 = sq_dist_rn(qx, qy, qz, sp);
+      sidx = (int)__float_as_uint(sp.w);
+      hit = d2 < r2;
+    }
+    const unsigned m = (__ballot_sync(0xffffffffu, hit) >> (16 * hw)) & 0xffffu;
+    const int pos = n + __popc(m & below);
+    if (hit && pos < kNbListCap2) {
+      list[slot][pos].d2 = d2;
+      list[slot][pos].idx = sidx;
+    }
+    n += __popc(m);
+  }
+  if (qvalid && hl == 0) {
+    if (counts != nullptr) counts[qi] = n;
+    if (out_max != nullptr) atomicMax(out_max, n);
+  }
+  __syncwarp();
+  int* row = out_idx + (size_t)qi * cols;
+
+  // ---- fast path: 64-key bitonic sort of unique 32-bit keys, both queries of the warp together ---------------
+  bool done = !qvalid;
+  {
+    const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+    const bool mine = qvalid && n <= 64;
+    unsigned k[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int i = 4 * hl + e;
+      k[e] = (mine && i < n) ? ((__float_as_uint(list[slot][i].d2) & ~63u) | (unsigned)i) : 0xffffffffu;
+    }
+    const int nsort = min(nmax, 64);
+    const int kmax = nsort <= 2 ? 2 : 2 << (31 - __clz(nsort - 1));   // warp-uniform
+    if (kmax >= 2) bitonic_block4<2>(k, hl);
+    if (kmax >= 4) bitonic_block4<4>(k, hl);
+    if (kmax >= 8) bitonic_block4<8>(k, hl);
+    if (kmax >= 16) bitonic_block4<16>(k, hl);
+    if (kmax >= 32) bitonic_block4<32>(k, hl);
+    if (kmax >= 64) bitonic_block4<64>(k, hl);
+    const unsigned next0 = __shfl_down_sync(0xffffffffu, k[0], 1, 16);
+    const int i0 = 4 * hl;
+    bool clash = (i0 + 1 < n && ((k[0] ^ k[1]) < 64u)) || (i0 + 2 < n && ((k[1] ^ k[2]) < 64u)) ||
+                 (i0 + 3 < n && ((k[2] ^ k[3]) < 64u)) || (i0 + 4 < n && hl < 15 && ((k[3] ^ next0) < 64u));
+    const bool any_clash = ((__ballot_sync(0xffffffffu, mine && clash) >> (16 * hw)) & 0xffffu) != 0u;
+    if (mine && !any_clash) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = i0 + e;
+        if (i < n && i < cols) row[i] = list[slot][k[e] & 63u].idx;
+      }
+      done = true;
+    }
+  }
+  // ---- exact paths, per half-warp ------------------------------------------------------------------------------
+  if (!done) {
+    if (n <= kNbListCap2) {
+      // rank sort: rank = number of hits that precede in (d2, idx)
+      for (int j = hl; j < n; j += 16) {
+        const float dj = list[slot][j].d2;
+        const int ij = list[slot][j].idx;
+        int rank = 0;
+        for (int kk = 0; kk < n; ++kk) rank += hit_less(list[slot][kk].d2, list[slot][kk].idx, dj, ij) ? 1 : 0;
+        if (rank < cols) row[rank] = ij;
+      }
+    } else {
+      // very dense rows: emit the nearest `cols` one at a time by re-scanning the runs
+      float last_d = -1.f;
+      int last_i = -1;
+      const int emit = min(n, cols);
+      for (int c = 0; c < emit; ++c) {
+        float best_d = 3.0e38f;
+        int best_i = 0x7fffffff;
+        for (int t = hl; t < T; t += 16) {
+          int r = 0;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) r += (t >= run_tab[slot][kk].x) ? 1 : 0;
+          const float4 sp = sorted_pts[t + run_tab[slot][r].y];
+          const float d2 = sq_dist_rn(qx, qy, qz, sp);
+          const int si = (int)__float_as_uint(sp.w);
+          if (d2 < r2 && hit_less(last_d, last_i, d2, si) && hit_less(d2, si, best_d, best_i)) {
+            best_d = d2;
+            best_i = si;
+          }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          const float od = __shfl_xor_sync(hmask, best_d, o);
+          const int oi = __shfl_xor_sync(hmask, best_i, o);
+          if (hit_less(od, oi, best_d, best_i)) {
+            best_d = od;
+            best_i = oi;
+          }
+        }
+        if (hl == 0) row[c] = best_i;
+        last_d = best_d;
+        last_i = best_i;
+      }
+    }
+  }
+  if (qvalid)
+    for (int c = n + hl; c < cols; c += 16) row[c] = pad_value;
+}
+
 static int query_common(bool fill, const float* queries, const int* q_batch_len, int Nq, int B, int Ns, float radius,
                         const float* host_bbox, const void* workspace, int cols, int pad_value, int* counts,
                         int* out_max, int* out_idx, cudaStream_t stream, const int* nq_dev = nullptr,
@@ -432,6 +645,16 @@ static int query_common(bool fill, const float* queries, const int* q_batch_len,
   if (Nq == 0) return D3F_OK;
   float r2 = radius * radius;  // neighbors.cpp:226 (fp32 product)
   int blocks = ceil_div(Nq, kNbWarps);
+  // two queries per warp by default (step 3.09 -> 3.02 ms, 1 M-point search 0.85 -> 0.76 ms); D3F_NB_HALFWARP=0
+  // selects the one-query-per-warp kernel (read per call: tests run both)
+  const char* hv = getenv("D3F_NB_HALFWARP");
+  if (fill && !(hv != nullptr && hv[0] == '0')) {
+    radius_query2_kernel<<<ceil_div(Nq, kNbWarps * 2), kNbWarps * 32, 0, stream>>>(
+        queries, Nq, nq_dev, w.q_start, B, g, w.sorted_pts, w.cell_start, r2, cols, pad_value, pad_dev, counts, out_max,
+        out_idx);
+    D3F_LAUNCH_CHECK("radius_query2_kernel");
+    return D3F_OK;
+  }
   if (fill) {
     radius_query_kernel<true><<<blocks, kNbWarps * 32, 0, stream>>>(queries, Nq, nq_dev, w.q_start, B, g, w.sorted_pts,
                                                                     w.cell_start, r2, cols, pad_value, pad_dev,

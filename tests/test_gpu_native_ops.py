@@ -58,9 +58,13 @@ def test_cpp_subsampling_compute_features_classes(cuda, golden):
         cpp_subsampling.compute(g["w_points"], features=g["w_features"][:10], sampleDl=0.1)
 
 
+@pytest.mark.parametrize("halfwarp", ["1", "0"])
 @pytest.mark.parametrize("name", ["demo", "frag", "lattice"])
-def test_neighbors_match_golden(cuda, golden, name):
+def test_neighbors_match_golden(cuda, golden, name, halfwarp, monkeypatch):
+    """Both query kernels (two queries per warp = the default, one query per warp = D3F_NB_HALFWARP=0) against the
+    reference's rows: real scan data, stacked fragments, and the lattice whose exact d2 ties force the exact sort."""
     from d3feat_b200 import tf_custom_ops as ops
+    monkeypatch.setenv("D3F_NB_HALFWARP", halfwarp)
     g = golden("neighbors_demo.npz" if name == "demo" else "synthetic.npz")
     if name == "demo":
         P, L, ref, r = g["points"], g["lengths"], g["neighbors"], float(g["radius"])
@@ -136,9 +140,11 @@ def test_edge_cases(cuda):
     assert np.array_equal(out2, out)
 
 
-def test_dense_rows_take_the_generic_path(cuda):
+@pytest.mark.parametrize("halfwarp", ["1", "0"])
+def test_dense_rows_take_the_generic_path(cuda, halfwarp, monkeypatch):
     """> 512 hits per query (shared-memory list overflows): the re-scan path must give the same rows."""
     from d3feat_b200 import tf_custom_ops as ops
+    monkeypatch.setenv("D3F_NB_HALFWARP", halfwarp)
     rng = np.random.default_rng(3)
     P = rng.uniform(0, 0.2, (1500, 3)).astype(np.float32)
     L = np.array([1500], np.int32)
