@@ -918,22 +918,22 @@ static int launch_stage1(int K, const Stage1Params& p, cudaStream_t stream) {
     const bool fast = p.influence == D3F_INFLUENCE_LINEAR && !p.closest;
     static const bool no_pared = [] { const char* v = getenv("D3F_S1_PARED"); return v != nullptr && v[0] == '0'; }();
     if (fast && !DEFORM && !no_pared && (long long)(p.Ns + 1) * p.Cin < (1ll << 31)) {
-      // Cin >= 256 (levels 3-4: a few thousand queries): one warp per (query, 128-channel pass) instead of a warp
-      // walking the passes one after the other, as long as the queries alone do not fill the machine
-      const int passes = p.Cin / 128;
-      const dim3 grid16(blocks, passes > 1 && blocks < 8 * kNumSMs ? passes : 1);
+      // Wide layers (Cin >= 128: levels 2-4, 15k queries and fewer) run as 64-channel passes spread over gridDim.y:
+      // one warp per (query, pass). Measured against 128-channel passes (NT = 16: 153 registers, 12 warps per SM,
+      // 26 % issue utilisation): 128->128 @ 15k 0.155 -> 0.143 ms, 256->256 @ 4k 0.125 -> 0.120, 512->512 @ 1.2k
+      // 0.117 -> 0.112 -- the re-evaluated correlation weights cost less than the occupancy gains.
       const char* sv = getenv("D3F_S1_STAGED");          // read per call: tests switch it
       const int staged = sv ? atoi(sv) : 0;
+      const dim3 grid_wide(blocks, p.Cin >= 128 ? p.Cin / 64 : 1);
       if (staged) {
         if (p.Cin == 32) kpconv_stage1_staged_kernel<4><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-        else if (p.Cin == 64) kpconv_stage1_staged_kernel<8><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-        else kpconv_stage1_staged_kernel<16><<<grid16, kS1Warps * 32, 0, stream>>>(p);
+        else kpconv_stage1_staged_kernel<8><<<grid_wide, kS1Warps * 32, 0, stream>>>(p);
         D3F_LAUNCH_CHECK("kpconv_stage1_staged_kernel");
         return D3F_OK;
       }
+      // (32-channel passes for Cin = 64 were measured too: 0.271 vs 0.260 ms at 60k queries -- worse)
       if (p.Cin == 32) kpconv_stage1_fast_kernel<4><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-      else if (p.Cin == 64) kpconv_stage1_fast_kernel<8><<<blocks, kS1Warps * 32, 0, stream>>>(p);
-      else kpconv_stage1_fast_kernel<16><<<grid16, kS1Warps * 32, 0, stream>>>(p);
+      else kpconv_stage1_fast_kernel<8><<<grid_wide, kS1Warps * 32, 0, stream>>>(p);
       D3F_LAUNCH_CHECK("kpconv_stage1_fast_kernel");
       return D3F_OK;
     }
