@@ -457,7 +457,7 @@ __device__ __forceinline__ void bitonic_block4(unsigned (&k)[4], int hl) {
   cex_dir(k[2], k[3], asc);
 }
 
-__global__ void __launch_bounds__(kNbWarps * 32)
+__global__ void __launch_bounds__(kNbWarps * 32, 6)
 radius_query2_kernel(const float* __restrict__ q, int Nq_cap, const int* __restrict__ nq_dev,
                      const int* __restrict__ q_start, int B, NbGrid g, const float4* __restrict__ sorted_pts,
                      const int* __restrict__ cell_start, float r2, int cols, int pad_value_in,
