@@ -1,12 +1,20 @@
 // KPConv forward (kernels/convolution_ops.py:161-255 rigid, :379-499 deformable).
 //
-// Stage 1 (this file): one warp per query point gathers the neighbour feature rows (coalesced row reads,
-// 128..512 B per warp request), evaluates the kernel-point correlation weights w[h,k] once per neighbour
-// (held in shared memory, read back as broadcast LDS.128) and accumulates
+// Stage 1 (this file): one warp per query point gathers the neighbour feature rows, evaluates the kernel-point
+// correlation weights w[h,k] and accumulates
 //        wf[n,k,:] = sum_h w[n,h,k] * feat[idx[n,h],:]            (:240 / :486)
-// in registers. Stage 2 is the dense contraction  out[n,:] = (sum_k wf[n,k,:] @ W[k]) / nn[n]  ==
-// [Nq, K*Cin] @ [K*Cin, Cout] with the block epilogue fused (gemm.cu). The [N,H,K,3], [N,H,K], [N,H,Cin]
-// intermediates of the TF graph are never materialised; wf is produced in query chunks that stay in L2.
+// Kernels, most specialised first (launch_stage1 picks):
+//   kpconv_stage1_fast_kernel<NT>    K = 15, rigid, linear influence, sum aggregation (every D3Feat model): weights in
+//                                    mma.sync A-fragment layout, rows loaded in B-fragment layout, 3xTF32 on the tensor
+//                                    pipe, nothing in shared memory; wide layers as 64-channel passes over gridDim.y
+//   kpconv_stage1_staged_kernel<NT>  the same with the gathers staged through shared memory (opt-in, same bits)
+//   kpconv_stage1_mma_kernel<...>    the general mma.sync kernel: deformable, gaussian / constant influence, closest mode
+//   kpconv_cin1_kernel<FAST>         first layer (Cin = 1), whole operator in one kernel
+//   kpconv_stage1_anyk_kernel, _v2_kernel, _kernel   CUDA-core paths: any number of kernel points, odd widths
+// Stage 2 is the dense contraction  out[n,:] = (sum_k wf[n,k,:] @ W[k]) / nn[n]  ==  [Nq, K*Cin] @ [K*Cin, Cout] on
+// tcgen05 with the block epilogue fused (tc_gemm.cu; gemm.cu without tensor cores). The [N,H,K,3], [N,H,K], [N,H,Cin]
+// intermediates of the TF graph are never materialised; wf is one buffer per layer (chunks beyond 512 MB).
+// kpconv_fused.cu holds the single persistent kernel (stage 1 + contraction) for the Cin = Cout = 32 layers (opt-in).
 #include <stdlib.h>
 
 #include "ops.cuh"
